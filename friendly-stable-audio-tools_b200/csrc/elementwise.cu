@@ -1,0 +1,415 @@
+// Bandwidth-bound kernels of the DiT / Oobleck path: LayerNorm, SnakeBeta, layout
+// changes around the transformer, timestep features, tiny conditioning MLPs, CFG.
+// All fp32 math; 128-bit global accesses where the layout allows.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace satb {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ----------------------------------------------------------------- LayerNorm
+// models/transformer.py:188-206 (F.layer_norm, eps 1e-5, learnable gamma, zero beta
+// buffer) with the optional adaLN modulation of :670-672 / :683-684 folded in.
+// One warp per row, the row lives in registers (two-pass mean / variance).
+constexpr int kLnMaxVec = 16;  // D <= 16 * 128 = 2048
+
+template <bool BF16>
+__global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, uint16_t* __restrict__ out,
+                                                        int rows, int D, const float* __restrict__ scale,
+                                                        const float* __restrict__ shift, int64_t mod_stride,
+                                                        int rows_per_item, int n_items) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nv = D >> 7;  // float4 per lane
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+  float4 v[kLnMaxVec];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    if (i < nv) {
+      v[i] = xr[lane + 32 * i];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(sum) / static_cast<float>(D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    if (i < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(D) + 1e-5f);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = beta ? reinterpret_cast<const float4*>(beta) : nullptr;
+  const float4* sc4 = nullptr;
+  const float4* sh4 = nullptr;
+  if (scale) {
+    const int item = (row / rows_per_item) % n_items;
+    sc4 = reinterpret_cast<const float4*>(scale + item * mod_stride);
+    sh4 = reinterpret_cast<const float4*>(shift + item * mod_stride);
+  }
+  uint2* o2 = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * D);
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    if (i < nv) {
+      const int idx = lane + 32 * i;
+      const float4 g = __ldg(g4 + idx);
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g.x;
+      y.y = (v[i].y - mean) * rstd * g.y;
+      y.z = (v[i].z - mean) * rstd * g.z;
+      y.w = (v[i].w - mean) * rstd * g.w;
+      if (b4) {
+        const float4 b = __ldg(b4 + idx);
+        y.x += b.x; y.y += b.y; y.z += b.z; y.w += b.w;
+      }
+      if (sc4) {
+        const float4 s = __ldg(sc4 + idx), t = __ldg(sh4 + idx);
+        y.x = y.x * (1.f + s.x) + t.x;
+        y.y = y.y * (1.f + s.y) + t.y;
+        y.z = y.z * (1.f + s.z) + t.z;
+        y.w = y.w * (1.f + s.w) + t.w;
+      }
+      o2[idx] = make_uint2(Op16<BF16>::pack(y.x, y.y), Op16<BF16>::pack(y.z, y.w));
+    }
+  }
+}
+
+// ----------------------------------------------------------------- SnakeBeta
+// models/blocks.py:318-319,350-358: y = x + sin^2(x * e^alpha) / (e^beta + 1e-9).
+__global__ void __launch_bounds__(256) snake_beta_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
+                                                         const float* __restrict__ beta, float* __restrict__ y, int C,
+                                                         int64_t T, int logscale) {
+  const int bc = blockIdx.y;
+  const int c = bc % C;
+  float a = __ldg(alpha + c), b = __ldg(beta + c);
+  if (logscale) {
+    a = expf(a);
+    b = expf(b);
+  }
+  const float inv_b = 1.0f / (b + 0.000000001f);
+  const float* xr = x + static_cast<size_t>(bc) * T;
+  float* yr = y + static_cast<size_t>(bc) * T;
+  const bool vec = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(xr) & 15) == 0) && ((reinterpret_cast<uintptr_t>(yr) & 15) == 0);
+  if (vec) {
+    const int64_t n4 = T >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(xr);
+    float4* y4 = reinterpret_cast<float4*>(yr);
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      float4 v = x4[i];
+      float s;
+      s = sinf(v.x * a); v.x = v.x + inv_b * (s * s);
+      s = sinf(v.y * a); v.y = v.y + inv_b * (s * s);
+      s = sinf(v.z * a); v.z = v.z + inv_b * (s * s);
+      s = sinf(v.w * a); v.w = v.w + inv_b * (s * s);
+      y4[i] = v;
+    }
+  } else {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < T;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const float v = xr[i];
+      const float s = sinf(v * a);
+      yr[i] = v + inv_b * (s * s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ DiT pre
+// NCL fp32 latent -> token-major 16-bit rows [R*N_seq, C]; the P leading rows of every
+// item (the prepend slots) are zero so the project_in GEMM leaves them 0.
+template <bool BF16>
+__global__ void __launch_bounds__(256) dit_pre_kernel(const float* __restrict__ x, uint16_t* __restrict__ a, int B_src,
+                                                      int C, int L, int P) {
+  __shared__ float tile[32][33];
+  const int r = blockIdx.z;
+  const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* xs = x + static_cast<size_t>(r % B_src) * C * L;
+  const int N_seq = L + P;
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, l = l0 + tx;
+    tile[j][tx] = (c < C && l < L) ? xs[static_cast<size_t>(c) * L + l] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int l = l0 + j, c = c0 + tx;
+    if (l < L && c < C)
+    {
+      typename Op16<BF16>::T hv = Op16<BF16>::from_float(tile[tx][j]);
+      a[(static_cast<size_t>(r) * N_seq + P + l) * C + c] = *reinterpret_cast<uint16_t*>(&hv);
+    }
+  }
+  if (blockIdx.x == 0 && P > 0) {
+    for (int j = ty; j < P; j += 8) {
+      const int c = c0 + tx;
+      if (c < C) a[(static_cast<size_t>(r) * N_seq + j) * C + c] = 0;
+    }
+  }
+}
+
+// --------------------------------------------------------- timestep features
+// models/blocks.py:95-97: f = (2*pi*t) * w (fp32), out = [cos f | sin f].
+__global__ void fourier_kernel(const float* __restrict__ t, const float* __restrict__ w, float* __restrict__ out, int B,
+                               int F) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * F) return;
+  const int b = i / F, j = i - b * F;
+  const float tt = 6.283185307179586f * t[b];
+  const float f = tt * w[j];
+  out[static_cast<size_t>(b) * 2 * F + j] = cosf(f);
+  out[static_cast<size_t>(b) * 2 * F + F + j] = sinf(f);
+}
+
+// --------------------------------------------------------------- skinny GEMM
+// Tiny-M linear layers (timestep / global embedding MLPs, adaLN projections):
+// one warp per output column, fp32 weights and accumulation, up to 8 rows per pass.
+__device__ __forceinline__ float silu_acc(float x) { return x / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restrict__ in, const float* __restrict__ W,
+                                                            const float* __restrict__ bias,
+                                                            const float* __restrict__ add, float* __restrict__ out,
+                                                            int R, int K, int N, int silu_in) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float* wr = W + static_cast<size_t>(n) * K;
+  for (int r0 = 0; r0 < R; r0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float w = __ldg(wr + k);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (r0 + j < R) {
+          float xv = in[static_cast<size_t>(r0 + j) * K + k];
+          if (silu_in) xv = silu_acc(xv);
+          acc[j] = fmaf(xv, w, acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = warp_sum(acc[j]);
+      if (lane == 0 && r0 + j < R) {
+        float v = s + (bias ? bias[n] : 0.f);
+        if (add) v += add[static_cast<size_t>(r0 + j) * N + n];
+        out[static_cast<size_t>(r0 + j) * N + n] = v;
+      }
+    }
+  }
+}
+
+__global__ void write_prepend_kernel(const float* __restrict__ tok, float* __restrict__ h, int B, int N_seq, int D) {
+  const int r = blockIdx.y;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < D) h[static_cast<size_t>(r) * N_seq * D + d] = tok[static_cast<size_t>(r % B) * D + d];
+}
+
+__global__ void gate_sigmoid_kernel(float* __restrict__ ssg, int depth, int D) {
+  // ssg: [rows, depth*6D]; transform gate columns (chunks 2 and 5 of every layer) to sigmoid(1 - g)
+  const int row = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over depth * 2 * D
+  if (i >= depth * 2 * D) return;
+  const int layer = i / (2 * D), rem = i - layer * 2 * D;
+  const int which = rem / D, d = rem - which * D;
+  float* p = ssg + static_cast<size_t>(row) * depth * 6 * D + static_cast<size_t>(layer) * 6 * D + (which ? 5 : 2) * D + d;
+  *p = 1.0f / (1.0f + expf(-(1.0f - *p)));
+}
+
+// ------------------------------------------------------------------ DiT post
+// models/dit.py:219 (drop prepend), :338-347 (CFG combine, std rescale over channels).
+// y rows are token-major [R*N_seq, C]; one thread per (b, l).
+__global__ void __launch_bounds__(128) dit_post_kernel(const float* __restrict__ y, float* __restrict__ out, int B,
+                                                       int C, int L, int N_seq, int P, int cfg, float cfg_scale,
+                                                       float scale_phi) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (l >= L) return;
+  const float* yc = y + (static_cast<size_t>(b) * N_seq + P + l) * C;
+  float* o = out + static_cast<size_t>(b) * C * L + l;
+  if (!cfg) {
+    for (int c = 0; c < C; ++c) o[static_cast<size_t>(c) * L] = yc[c];
+    return;
+  }
+  const float* yu = y + (static_cast<size_t>(B + b) * N_seq + P + l) * C;
+  if (scale_phi == 0.f) {
+    for (int c = 0; c < C; ++c) {
+      const float cv = yc[c], uv = yu[c];
+      o[static_cast<size_t>(c) * L] = uv + (cv - uv) * cfg_scale;
+    }
+    return;
+  }
+  // unbiased std over the channel dim of cond and of the cfg output (torch.std default)
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float cv = yc[c], uv = yu[c];
+    s1 += cv;
+    s2 += uv + (cv - uv) * cfg_scale;
+  }
+  const float m1 = s1 / C, m2 = s2 / C;
+  float v1 = 0.f, v2 = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float cv = yc[c], uv = yu[c];
+    const float g = uv + (cv - uv) * cfg_scale;
+    v1 += (cv - m1) * (cv - m1);
+    v2 += (g - m2) * (g - m2);
+  }
+  const float ratio = sqrtf(v1 / (C - 1)) / sqrtf(v2 / (C - 1));
+  for (int c = 0; c < C; ++c) {
+    const float cv = yc[c], uv = yu[c];
+    const float g = uv + (cv - uv) * cfg_scale;
+    o[static_cast<size_t>(c) * L] = scale_phi * (g * ratio) + (1.f - scale_phi) * g;
+  }
+}
+
+// ----------------------------------------------------------------- weight prep
+template <bool BF16>
+__global__ void cast_rows_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, const int* __restrict__ perm,
+                                 int rows, int cols, int64_t src_ld, int64_t dst_ld) {
+  const int r = blockIdx.y;
+  const int sr = perm ? perm[r] : r;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
+    typename Op16<BF16>::T h = Op16<BF16>::from_float(src[static_cast<size_t>(sr) * src_ld + c]);
+    dst[static_cast<size_t>(r) * dst_ld + c] = *reinterpret_cast<uint16_t*>(&h);
+  }
+}
+
+__global__ void gather_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, const int* __restrict__ perm,
+                                  int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[perm ? perm[i] : i];
+}
+
+}  // namespace
+
+int launch_layernorm(const float* x, const float* gamma, const float* beta, void* out16, int rows, int D,
+                     const float* scale, const float* shift, int64_t mod_stride, int rows_per_item, int n_items,
+                     bool bf16, cudaStream_t stream) {
+  SATB_REQUIRE(D % 128 == 0 && D <= kLnMaxVec * 128, "LayerNorm width must be a multiple of 128 and <= 2048");
+  if (rows <= 0) return 0;
+  const int grid = ceil_div(rows, 4);
+  if (bf16)
+    layernorm_kernel<true><<<grid, 128, 0, stream>>>(x, gamma, beta, static_cast<uint16_t*>(out16), rows, D, scale,
+                                                     shift, mod_stride, rows_per_item, n_items > 0 ? n_items : 1);
+  else
+    layernorm_kernel<false><<<grid, 128, 0, stream>>>(x, gamma, beta, static_cast<uint16_t*>(out16), rows, D, scale,
+                                                      shift, mod_stride, rows_per_item, n_items > 0 ? n_items : 1);
+  count_launch();
+  SATB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_snake_beta(const float* x, const float* alpha, const float* beta, float* y, int B, int C, int64_t T,
+                      int logscale, cudaStream_t stream) {
+  if (B <= 0 || C <= 0 || T <= 0) return 0;
+  SATB_REQUIRE(static_cast<int64_t>(B) * C <= 65535, "snake: B*C exceeds grid.y limit");
+  int64_t per_block = 256 * 4 * 4;
+  int gx = static_cast<int>(ceil_div64(T, per_block));
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, B * C);
+  snake_beta_kernel<<<grid, 256, 0, stream>>>(x, alpha, beta, y, C, T, logscale);
+  count_launch();
+  SATB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_dit_pre(const float* x, void* a16, int R, int B_src, int C, int L, int P, bool bf16, cudaStream_t stream) {
+  dim3 grid(ceil_div(L, 32), ceil_div(C, 32), R);
+  if (bf16)
+    dit_pre_kernel<true><<<grid, 256, 0, stream>>>(x, static_cast<uint16_t*>(a16), B_src, C, L, P);
+  else
+    dit_pre_kernel<false><<<grid, 256, 0, stream>>>(x, static_cast<uint16_t*>(a16), B_src, C, L, P);
+  count_launch();
+  SATB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_fourier(const float* t, const float* w, float* out, int B, int F, cudaStream_t stream) {
+  fourier_kernel<<<ceil_div(B * F, 128), 128, 0, stream>>>(t, w, out, B, F);
+  count_launch();
+  SATB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_skinny_linear(const float* in, const float* W, const float* bias, const float* add, float* out, int R,
+                         int K, int N, int silu_in, cudaStream_t stream) {
+  SATB_REQUIRE(R >= 1 && R <= 4096, "skinny linear: bad row count");
+  skinny_linear_kernel<<<ceil_div(N, 8), 256, 0, stream>>>(in, W, bias, add, out, R, K, N, silu_in);
+  count_launch();
+  SATB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_write_prepend(const float* tok, float* h, int R, int B, int N_seq, int D, cudaStream_t stream) {
+  dim3 grid(ceil_div(D, 256), R);
+  write_prepend_kernel<<<grid, 256, 0, stream>>>(tok, h, B, N_seq, D);
+  count_launch();
+  SATB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_gate_sigmoid(float* ssg, int rows, int depth, int D, cudaStream_t stream) {
+  dim3 grid(ceil_div(depth * 2 * D, 256), rows);
+  gate_sigmoid_kernel<<<grid, 256, 0, stream>>>(ssg, depth, D);
+  count_launch();
+  SATB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_dit_post(const float* y, float* out, int B, int C, int L, int N_seq, int P, int cfg, float cfg_scale,
+                    float scale_phi, cudaStream_t stream) {
+  dim3 grid(ceil_div(L, 128), B);
+  dit_post_kernel<<<grid, 128, 0, stream>>>(y, out, B, C, L, N_seq, P, cfg, cfg_scale, scale_phi);
+  count_launch();
+  SATB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_cast_rows(const float* src, void* dst, const int* perm, int rows, int cols, int64_t src_ld, int64_t dst_ld,
+                     bool bf16, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  int gx = ceil_div(cols, 256);
+  if (gx > 64) gx = 64;
+  for (int r0 = 0; r0 < rows; r0 += 65535) {
+    const int nr = rows - r0 < 65535 ? rows - r0 : 65535;
+    dim3 grid(gx, nr);
+    const float* s = perm ? src : src + static_cast<size_t>(r0) * src_ld;
+    uint16_t* d = static_cast<uint16_t*>(dst) + static_cast<size_t>(r0) * dst_ld;
+    const int* pm = perm ? perm + r0 : nullptr;
+    if (bf16)
+      cast_rows_kernel<true><<<grid, 256, 0, stream>>>(s, d, pm, nr, cols, src_ld, dst_ld);
+    else
+      cast_rows_kernel<false><<<grid, 256, 0, stream>>>(s, d, pm, nr, cols, src_ld, dst_ld);
+    count_launch();
+  }
+  SATB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_gather_f32(const float* src, float* dst, const int* perm, int n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  gather_f32_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(src, dst, perm, n);
+  count_launch();
+  SATB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_zero(void* p, size_t bytes, cudaStream_t stream) {
+  SATB_CHECK_CUDA(cudaMemsetAsync(p, 0, bytes, stream));
+  return 0;
+}
+
+}  // namespace satb

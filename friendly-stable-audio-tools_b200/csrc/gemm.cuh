@@ -1,0 +1,423 @@
+// tcgen05 / TMA / TMEM GEMM for sm_100a with fused epilogues.
+//
+//   C[row, n] = sum_{tap, k} A[batch, l + tap_base + tap*tap_step, k] * B[tap*b_tap_rows + n, k]
+//
+// A is a K-major 16-bit activation matrix viewed as (K, L, batches) through a
+// 3-D TMA tensor map (out-of-range rows are zero-filled by TMA, which is how
+// dilated-convolution padding and the ragged M tail are handled); B is the
+// K-major weight matrix [taps * N, K].  A plain Linear layer is n_taps = 1,
+// batches = 1.  Accumulation is fp32 in TMEM.
+//
+// Structure (one persistent CTA per SM, 256 threads):
+//   warp 0   TMA producer       global -> 128B-swizzled smem ring (mbarrier full/empty)
+//   warp 1   MMA issuer         one thread issues tcgen05.mma 128xBNx16, commits to mbarriers
+//   warp 2   TMEM allocator     2 x BN fp32 columns (double-buffered accumulator)
+//   warps 4-7 epilogue          tcgen05.ld 32 lanes x 32 columns -> registers -> fused op -> global
+// The accumulator is double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace satb {
+
+struct GemmShape {
+  int L;            // rows per batch
+  int batches;      // number of batches (1 for flat GEMMs)
+  int N;            // output columns
+  int K;            // reduction length per tap (multiple of 8)
+  int n_taps;       // 1 for Linear, 7 for conv k7, 2 for transposed conv phases
+  int tap_base;     // row offset of tap 0 (e.g. -3*dilation)
+  int tap_step;     // row offset increment per tap (dilation; -1 for transposed conv)
+  int b_tap_rows;   // rows of B per tap (= N padded as stored)
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;   // 64 x 16-bit = 128 B = one swizzle atom row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 256;
+constexpr int kSmemBudget = 220 * 1024;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageA = kBlockM * kBlockK * 2;
+  static constexpr int kStageB = BN * kBlockK * 2;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = (kSmemBudget - 1024) / kStage > 8 ? 8 : (kSmemBudget - 1024) / kStage;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(BN == 64 || BN == 128 || BN == 256, "BN must be 64/128/256");
+};
+
+struct EpiCtx {
+  int row;       // flattened output row = batch * L + l
+  int l;         // row within batch
+  int batch;
+  int col0;      // first output column of this register chunk
+  bool valid;    // row < L
+};
+
+template <class Epi, int BN, bool BF16>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmShape s, const typename Epi::Params ep) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStage);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (s.L + kBlockM - 1) / kBlockM;
+  const int n_tiles = (s.N + BN - 1) / BN;
+  const int tiles_per_n = m_tiles * s.batches;
+  const int total_tiles = tiles_per_n * n_tiles;
+  const int kb_per_tap = (s.K + kBlockK - 1) / kBlockK;
+  const int num_kb = kb_per_tap * s.n_taps;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile / tiles_per_n;
+        const int rem = tile - nt * tiles_per_n;
+        const int batch = rem / m_tiles;
+        const int m0 = (rem - batch * m_tiles) * kBlockM;
+        const int n0 = nt * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / kb_per_tap;
+          const int k0 = (kb - tap * kb_per_tap) * kBlockK;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStage;
+          uint8_t* sb = sa + Cfg::kStageA;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStage);
+          tma_load_3d(sa, &tmA, &full_bar[stage], k0, m0 + s.tap_base + tap * s.tap_step, batch);
+          tma_load_2d(sb, &tmB, &full_bar[stage], k0, tap * s.b_tap_rows + n0);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // -------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc = make_idesc_f16(kBlockM, BN, BF16);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStage);
+          const uint32_t b_addr = a_addr + Cfg::kStageA;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = make_desc_kmajor_sw128(a_addr + k * kUmmaK * 2);
+            const uint64_t db = make_desc_kmajor_sw128(b_addr + k * kUmmaK * 2);
+            umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp - 4;  // TMEM lane quadrant == warp % 4
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile / tiles_per_n;
+      const int rem = tile - nt * tiles_per_n;
+      const int batch = rem / m_tiles;
+      const int m0 = (rem - batch * m_tiles) * kBlockM;
+      const int n0 = nt * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      EpiCtx c;
+      c.l = m0 + q * 32 + lane;
+      c.batch = batch;
+      c.row = batch * s.L + c.l;
+      c.valid = c.l < s.L;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += Epi::kCols) {
+        if (n0 + cc >= s.N) break;   // warp-uniform
+        uint32_t r[Epi::kCols];
+#pragma unroll
+        for (int j = 0; j < Epi::kCols / 32; ++j) {
+          uint32_t(&rj)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[j * 32]);
+          tmem_ld_32x32(t_row + cc + j * 32, rj);
+        }
+        tmem_ld_wait();
+        c.col0 = n0 + cc;
+        Epi::apply(ep, c, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ epilogues
+// Every epilogue receives kCols consecutive fp32 accumulator columns of one row
+// (as raw bits in r[]) and writes them straight to global memory.
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+// out16[row, col] = act(acc + bias)   (act: 0 none, 1 SiLU)
+template <bool BF16>
+struct EpiStore16 {
+  static constexpr int kCols = 32;
+  struct Params {
+    void* out;
+    int ld;
+    const float* bias;  // may be null
+    int act;
+  };
+  __device__ static __forceinline__ void apply(const Params& p, const EpiCtx& c, const uint32_t (&r)[32]) {
+    if (!c.valid) return;
+    uint32_t o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
+      if (p.bias) {
+        a += __ldg(p.bias + c.col0 + 2 * j);
+        b += __ldg(p.bias + c.col0 + 2 * j + 1);
+      }
+      if (p.act == 1) {
+        a = silu_f(a);
+        b = silu_f(b);
+      }
+      o[j] = Op16<BF16>::pack(a, b);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + static_cast<size_t>(c.row) * p.ld + c.col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+  }
+};
+
+// out32[row, col] = acc (+ bias)
+struct EpiStore32 {
+  static constexpr int kCols = 32;
+  struct Params {
+    float* out;
+    int ld;
+    const float* bias;
+  };
+  __device__ static __forceinline__ void apply(const Params& p, const EpiCtx& c, const uint32_t (&r)[32]) {
+    if (!c.valid) return;
+    float4* dst = reinterpret_cast<float4*>(p.out + static_cast<size_t>(c.row) * p.ld + c.col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                             __uint_as_float(r[4 * j + 3]));
+      if (p.bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c.col0) + j);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      }
+      dst[j] = v;
+    }
+  }
+};
+
+// Residual stream update (models/transformer.py:692-700 and adaLN :670-689):
+//   h[row, col] += (acc + bias[col]) * gate[row / rows_per_item, col]
+struct EpiResidual {
+  static constexpr int kCols = 32;
+  struct Params {
+    float* h;
+    int ld;
+    const float* bias;  // may be null
+    const float* gate;  // may be null; sigmoid(1 - gate) precomputed, row stride gate_ld
+    int rows_per_item;
+    int gate_ld;
+    int n_items;        // item = (row / rows_per_item) % n_items (CFG halves share the conditioning)
+  };
+  __device__ static __forceinline__ void apply(const Params& p, const EpiCtx& c, const uint32_t (&r)[32]) {
+    if (!c.valid) return;
+    float4* dst = reinterpret_cast<float4*>(p.h + static_cast<size_t>(c.row) * p.ld + c.col0);
+    const float4* g = p.gate ? reinterpret_cast<const float4*>(
+                                   p.gate + static_cast<size_t>((c.row / p.rows_per_item) % p.n_items) * p.gate_ld + c.col0)
+                             : nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                             __uint_as_float(r[4 * j + 3]));
+      if (p.bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c.col0) + j);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      }
+      if (g) {
+        const float4 gg = __ldg(g + j);
+        v.x *= gg.x; v.y *= gg.y; v.z *= gg.z; v.w *= gg.w;
+      }
+      float4 o = dst[j];
+      o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+      dst[j] = o;
+    }
+  }
+};
+
+// Fused QKV projection epilogue: split is implicit (q | k | v are column ranges of
+// one [M, 3D] buffer); partial rotary on the first 32 dims of every 64-wide q and k
+// head (models/transformer.py:158-183,438-452): pairs (i, i+16), position = token
+// index within the sequence (prepend token = position 0).  fp32 math, then cast.
+template <bool BF16>
+struct EpiQkvRope {
+  static constexpr int kCols = 32;
+  struct Params {
+    void* out;
+    int ld;            // 3*D
+    int rope_cols;     // 2*D : columns >= this (v) are never rotated
+    int seq_len;       // tokens per item (position = row % seq_len)
+    const float* cos_tab;  // [seq_len, 16]
+    const float* sin_tab;  // [seq_len, 16]
+  };
+  __device__ static __forceinline__ void apply(const Params& p, const EpiCtx& c, const uint32_t (&r)[32]) {
+    if (!c.valid) return;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    // chunk of 32 columns aligned to 32: even chunks of a 64-wide head are the rotary dims
+    if (c.col0 < p.rope_cols && ((c.col0 >> 5) & 1) == 0 && p.cos_tab) {
+      const int pos = c.row % p.seq_len;
+      const float4* ct = reinterpret_cast<const float4*>(p.cos_tab + pos * 16);
+      const float4* st = reinterpret_cast<const float4*>(p.sin_tab + pos * 16);
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 cs = __ldg(ct + j4), sn = __ldg(st + j4);
+        const float cc[4] = {cs.x, cs.y, cs.z, cs.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j4 * 4 + u;
+          const float a = v[j], b = v[j + 16];
+          v[j] = a * cc[u] - b * ss[u];       // t*cos + rotate_half(t)*sin, rotate_half = [-b, a]
+          v[j + 16] = b * cc[u] + a * ss[u];
+        }
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + static_cast<size_t>(c.row) * p.ld + c.col0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      dst[j] = make_uint4(Op16<BF16>::pack(v[8 * j], v[8 * j + 1]), Op16<BF16>::pack(v[8 * j + 2], v[8 * j + 3]),
+                          Op16<BF16>::pack(v[8 * j + 4], v[8 * j + 5]), Op16<BF16>::pack(v[8 * j + 6], v[8 * j + 7]));
+  }
+};
+
+// SwiGLU epilogue (models/transformer.py:232-235: value = first half, gate = second
+// half of the projection).  The weight rows are interleaved at load time so every
+// 64-column group holds 32 value columns followed by their 32 gate columns:
+//   out[row, g*32 + j] = (acc[g*64 + j] + b) * silu(acc[g*64 + 32 + j] + b')
+template <bool BF16>
+struct EpiSwiglu {
+  static constexpr int kCols = 64;
+  struct Params {
+    void* out;
+    int ld;             // inner dim (N/2)
+    const float* bias;  // interleaved like the weight rows; may be null
+  };
+  __device__ static __forceinline__ void apply(const Params& p, const EpiCtx& c, const uint32_t (&r)[64]) {
+    if (!c.valid) return;
+    uint32_t o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float a0 = __uint_as_float(r[2 * j]), a1 = __uint_as_float(r[2 * j + 1]);
+      float g0 = __uint_as_float(r[32 + 2 * j]), g1 = __uint_as_float(r[33 + 2 * j]);
+      if (p.bias) {
+        a0 += __ldg(p.bias + c.col0 + 2 * j);
+        a1 += __ldg(p.bias + c.col0 + 2 * j + 1);
+        g0 += __ldg(p.bias + c.col0 + 32 + 2 * j);
+        g1 += __ldg(p.bias + c.col0 + 33 + 2 * j);
+      }
+      o[j] = Op16<BF16>::pack(a0 * silu_f(g0), a1 * silu_f(g1));
+    }
+    uint4* dst =
+        reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + static_cast<size_t>(c.row) * p.ld + (c.col0 >> 1));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+  }
+};
+
+// ------------------------------------------------------------------ host side
+int make_tmap_a(CUtensorMap* m, const void* ptr, int K, int L, int batches, int64_t row_stride_elems,
+                int64_t batch_stride_elems);
+int make_tmap_b(CUtensorMap* m, const void* ptr, int K, int rows, int64_t row_stride_elems, int box_rows);
+
+template <class Epi, int BN, bool BF16>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const typename Epi::Params& ep,
+                cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_tcgen05_kernel<Epi, BN, BF16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int m_tiles = ceil_div(s.L, kBlockM), n_tiles = ceil_div(s.N, BN);
+  const int total = m_tiles * s.batches * n_tiles;
+  if (total <= 0) return 0;
+  int grid = device_sm_count();
+  if (grid > total) grid = total;
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, s, ep);
+  count_launch();
+  SATB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace satb

@@ -1,0 +1,41 @@
+// Internal launch API between translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace satb {
+
+// ---- attention.cu
+int launch_attention(const void* q, const void* k, const void* v, void* o, int64_t ldq, int64_t ldk, int64_t ldv,
+                     int64_t ldo, int64_t q_bs, int64_t k_bs, int64_t v_bs, int64_t o_bs, int batch, int H, int H_kv,
+                     int Nq, int Nk, int head_dim, bool bf16, cudaStream_t stream);
+
+// ---- elementwise.cu
+// LayerNorm over the last dim (eps 1e-5), optional adaLN modulation y*(1+scale)+shift, 16-bit output.
+int launch_layernorm(const float* x, const float* gamma, const float* beta, void* out16, int rows, int D,
+                     const float* scale, const float* shift, int64_t mod_stride, int rows_per_item, int n_items,
+                     bool bf16, cudaStream_t stream);
+// SnakeBeta on [B, C, T] fp32 (log-scale alpha/beta per channel).
+int launch_snake_beta(const float* x, const float* alpha, const float* beta, float* y, int B, int C, int64_t T,
+                      int logscale, cudaStream_t stream);
+// x[B_src, C, L] fp32 -> a16[(r*N_seq + P + l), c] (rows r*N_seq .. +P-1 zero), r < R, source row r % B_src.
+int launch_dit_pre(const float* x, void* a16, int R, int B_src, int C, int L, int P, bool bf16, cudaStream_t stream);
+// Fourier timestep features [B, 2*F]: cat(cos(2*pi*t*w), sin(2*pi*t*w)).
+int launch_fourier(const float* t, const float* w, float* out, int B, int F, cudaStream_t stream);
+// out[r, n] = sum_k act_in(in[r, k]) * W[n, k] + bias[n] (+ add[r, n]); fp32 weights, R <= 64.
+int launch_skinny_linear(const float* in, const float* W, const float* bias, const float* add, float* out, int R,
+                         int K, int N, int silu_in, cudaStream_t stream);
+// h[(r*N_seq), :] = tok[r % B, :]  (the prepended global-conditioning token)
+int launch_write_prepend(const float* tok, float* h, int R, int B, int N_seq, int D, cudaStream_t stream);
+// in place: x = sigmoid(1 - x) on column ranges [c0, c0+D) and [c1, c1+D) of every 6D-wide layer block
+int launch_gate_sigmoid(float* ssg, int rows, int depth, int D, cudaStream_t stream);
+// y[R*N_seq, C] fp32 -> out[B, C, L] with CFG combine / rescale (models/dit.py:338-347)
+int launch_dit_post(const float* y, float* out, int B, int C, int L, int N_seq, int P, int cfg, float cfg_scale,
+                    float scale_phi, cudaStream_t stream);
+// generic fp32 -> 16-bit cast with row gather: dst[r, :] = src[perm ? perm[r] : r, :] * row_scale
+int launch_cast_rows(const float* src, void* dst, const int* perm, int rows, int cols, int64_t src_ld, int64_t dst_ld,
+                     bool bf16, cudaStream_t stream);
+int launch_gather_f32(const float* src, float* dst, const int* perm, int n, cudaStream_t stream);
+int launch_zero(void* p, size_t bytes, cudaStream_t stream);
+
+}  // namespace satb

@@ -1,0 +1,89 @@
+// Host-side runtime pieces shared by all kernels: error string, SM count, launch
+// counter and TMA tensor-map construction (driver entry point fetched through the
+// runtime so the library does not link libcuda and loads on CPU-only machines).
+#include <mutex>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace satb {
+
+static thread_local std::string g_last_error;
+unsigned long long g_launch_count = 0;
+
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const char* get_last_error() { return g_last_error.c_str(); }
+
+int device_sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    if (cached <= 0) cached = 148;
+  }
+  return cached;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// A operand: 16-bit, dims (K, L, batches), box (64, 128, 1), 128B swizzle, zero OOB fill.
+int make_tmap_a(CUtensorMap* m, const void* ptr, int K, int L, int batches, int64_t row_stride_elems,
+                int64_t batch_stride_elems) {
+  EncodeTiledFn fn = get_encode_fn();
+  SATB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  SATB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base must be 16B aligned");
+  SATB_REQUIRE((row_stride_elems * 2) % 16 == 0 && (batch_stride_elems * 2) % 16 == 0, "TMA strides must be 16B multiples");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(batches)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_stride_elems) * 2, static_cast<cuuint64_t>(batch_stride_elems) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(kBlockM), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(A) failed with CUresult " + std::to_string(static_cast<int>(r)) +
+                   " K=" + std::to_string(K) + " L=" + std::to_string(L) + " batches=" + std::to_string(batches) +
+                   " rs=" + std::to_string(row_stride_elems) + " bs=" + std::to_string(batch_stride_elems));
+    return -3;
+  }
+  return 0;
+}
+
+// B operand (weights): 16-bit, dims (K, rows), box (64, box_rows), 128B swizzle.
+int make_tmap_b(CUtensorMap* m, const void* ptr, int K, int rows, int64_t row_stride_elems, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  SATB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  SATB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base must be 16B aligned");
+  SATB_REQUIRE((row_stride_elems * 2) % 16 == 0, "TMA strides must be 16B multiples");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(row_stride_elems) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(B) failed with CUresult " + std::to_string(static_cast<int>(r)) +
+                   " K=" + std::to_string(K) + " rows=" + std::to_string(rows));
+    return -3;
+  }
+  return 0;
+}
+
+}  // namespace satb

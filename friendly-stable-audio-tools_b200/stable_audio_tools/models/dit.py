@@ -1,0 +1,214 @@
+"""DiffusionTransformer: the reference's module interface over the native DiT kernels.
+
+Interface parity with reference ``models/dit.py:14-364`` (constructor kwargs, submodule
+and parameter names, ``forward`` signature and CFG semantics); the arithmetic runs in
+``libsatb200.so`` (``satb_dit_*`` in include/satb200.h):
+
+* step-invariant conditioning work (``to_cond_embed``, ``to_global_embed``, every layer's
+  cross-attention k/v; dit.py:149-154, transformer.py:425) is hoisted into
+  ``satb_dit_prepare_cond`` and cached while the same conditioning tensors are passed;
+* one ``forward`` = one ``satb_dit_forward`` call: batched CFG rows (cond first, uncond
+  second, dit.py:270-320), 24 blocks, CFG combine / rescale (dit.py:338-347);
+* rows whose context is all-zero (the uncond half without a negative prompt) skip
+  cross-attention: the branch is bias-free, so its output is exactly 0.
+
+There is no eager / CPU fallback: tensors must live on a CUDA device.
+"""
+import ctypes
+import typing as tp
+
+import torch
+from torch import nn
+
+from .. import _native
+from .blocks import FourierFeatures
+from .transformer import ContinuousTransformer
+
+
+class DiffusionTransformer(nn.Module):
+    def __init__(self,
+                 io_channels: int = 32,
+                 patch_size: int = 1,
+                 embed_dim: int = 768,
+                 cond_token_dim: int = 0,
+                 project_cond_tokens: bool = True,
+                 global_cond_dim: int = 0,
+                 project_global_cond: bool = True,
+                 input_concat_dim: int = 0,
+                 prepend_cond_dim: int = 0,
+                 depth: int = 12,
+                 num_heads: int = 8,
+                 transformer_type: str = "x-transformers",
+                 global_cond_type: str = "prepend",
+                 operand_dtype: str = "fp16",
+                 **kwargs):
+        super().__init__()
+        if transformer_type != "continuous_transformer":
+            raise NotImplementedError("only transformer_type='continuous_transformer' is on the native hot path "
+                                      "(the reference's x-transformers branch needs an un-vendored dependency)")
+        if patch_size != 1 or input_concat_dim != 0 or prepend_cond_dim != 0:
+            raise NotImplementedError("patch_size>1 / input_concat / prepend_cond are not on the native hot path yet")
+        if global_cond_type not in ("prepend", "adaLN"):
+            raise ValueError(f"unknown global_cond_type {global_cond_type}")
+        self.patch_size = patch_size
+        self.cond_token_dim = cond_token_dim
+        self.input_concat_dim = input_concat_dim
+        self.io_channels = io_channels
+        self.embed_dim = embed_dim
+        self.depth = depth
+        self.num_heads = num_heads
+        self.global_cond_dim = global_cond_dim
+        self.project_cond_tokens = project_cond_tokens
+        self.project_global_cond = project_global_cond
+        self.transformer_type = transformer_type
+        self.global_cond_type = global_cond_type
+        self.operand_dtype = operand_dtype
+
+        feat_dim = 256
+        self.timestep_features = FourierFeatures(1, feat_dim)
+        self.to_timestep_embed = nn.Sequential(nn.Linear(feat_dim, embed_dim, bias=True), nn.SiLU(),
+                                               nn.Linear(embed_dim, embed_dim, bias=True))
+        cond_embed_dim = 0
+        if cond_token_dim > 0:
+            cond_embed_dim = embed_dim if project_cond_tokens else cond_token_dim
+            self.to_cond_embed = nn.Sequential(nn.Linear(cond_token_dim, cond_embed_dim, bias=False), nn.SiLU(),
+                                               nn.Linear(cond_embed_dim, cond_embed_dim, bias=False))
+        if global_cond_dim > 0:
+            glob_embed_dim = embed_dim if project_global_cond else global_cond_dim
+            self.to_global_embed = nn.Sequential(nn.Linear(global_cond_dim, glob_embed_dim, bias=False), nn.SiLU(),
+                                                 nn.Linear(glob_embed_dim, glob_embed_dim, bias=False))
+        self.transformer = ContinuousTransformer(
+            dim=embed_dim, depth=depth, dim_heads=embed_dim // num_heads, dim_in=io_channels * patch_size,
+            dim_out=io_channels * patch_size, cross_attend=cond_token_dim > 0, cond_token_dim=cond_embed_dim,
+            global_cond_dim=embed_dim if global_cond_type == "adaLN" else None, **kwargs)
+        self.preprocess_conv = nn.Conv1d(io_channels, io_channels, 1, bias=False)
+        nn.init.zeros_(self.preprocess_conv.weight)
+        self.postprocess_conv = nn.Conv1d(io_channels, io_channels, 1, bias=False)
+        nn.init.zeros_(self.postprocess_conv.weight)
+
+        # native state (not part of the state dict)
+        self.__dict__["_h"] = None
+        self.__dict__["_weights_dirty"] = True
+        self.__dict__["_cond_key"] = None
+        self.__dict__["_keepalive"] = None
+
+    # ------------------------------------------------------------------ native plumbing
+    def _apply(self, fn, *a, **k):
+        self.__dict__["_weights_dirty"] = True
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self.__dict__["_weights_dirty"] = True
+        return super().load_state_dict(*a, **k)
+
+    def refresh_native_weights(self):
+        """Call after mutating parameters in place (``load_state_dict`` / ``.to()`` do it for you)."""
+        self.__dict__["_weights_dirty"] = True
+
+    def __del__(self):
+        h = self.__dict__.get("_h")
+        if h is not None:
+            try:
+                _native.lib().satb_dit_destroy(h)
+            except Exception:
+                pass
+
+    def _handle(self, device):
+        lib = _native.lib()
+        if self.__dict__["_h"] is None:
+            cfg = _native.SatbDitConfig(
+                io_channels=self.io_channels, embed_dim=self.embed_dim, depth=self.depth, num_heads=self.num_heads,
+                cond_token_dim=self.cond_token_dim, global_cond_dim=self.global_cond_dim,
+                project_cond_tokens=int(self.project_cond_tokens), project_global_cond=int(self.project_global_cond),
+                global_cond_type=1 if self.global_cond_type == "adaLN" else 0, patch_size=self.patch_size,
+                operand_dtype=1 if self.operand_dtype == "bf16" else 0)
+            h = ctypes.c_void_p()
+            _native.check(lib.satb_dit_create(ctypes.byref(cfg), ctypes.byref(h)))
+            self.__dict__["_h"] = h
+        if self.__dict__["_weights_dirty"]:
+            st = _native.stream_ptr(device)
+            with torch.no_grad():
+                for name, t in self.state_dict().items():
+                    if name.endswith("rotary_pos_emb.scale") or t is None:
+                        continue
+                    if not t.is_cuda:
+                        raise _native.NativeError(
+                            f"parameter {name} is on {t.device}: move the model to a CUDA device "
+                            "(this package has no CPU path)")
+                    src = t.detach().to(torch.float32).contiguous()
+                    _native.check(lib.satb_dit_load_weight(self.__dict__["_h"], name.encode(), _native.ptr(src),
+                                                           src.numel(), st))
+                _native.check(lib.satb_dit_finalize(self.__dict__["_h"], st))
+            self.__dict__["_weights_dirty"] = False
+            self.__dict__["_cond_key"] = None
+        return self.__dict__["_h"]
+
+    @staticmethod
+    def _tkey(t):
+        return None if t is None else (t.data_ptr(), t._version, tuple(t.shape), str(t.dtype))
+
+    def _prepare(self, h, cross, neg, glob, use_cfg, device, B):
+        key = (self._tkey(cross), self._tkey(neg), self._tkey(glob), bool(use_cfg), B)
+        if key == self.__dict__["_cond_key"]:
+            return
+        f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
+        c, n, g = f32(cross), f32(neg), f32(glob)
+        for name, tt in (("cross_attn_cond", c), ("negative_cross_attn_cond", n), ("global_embed", g)):
+            if tt is not None and tt.shape[0] != B:
+                raise ValueError(f"{name} batch {tt.shape[0]} != input batch {B}")
+        Mctx = c.shape[1] if c is not None else 0
+        _native.check(_native.lib().satb_dit_prepare_cond(h, _native.ptr(c), _native.ptr(n), _native.ptr(g), B, Mctx,
+                                                          1 if use_cfg else 0, _native.stream_ptr(device)))
+        self.__dict__["_cond_key"] = key
+        self.__dict__["_keepalive"] = (cross, neg, glob)   # keep the keyed storage alive
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, x, t, cross_attn_cond=None, cross_attn_cond_mask=None, negative_cross_attn_cond=None,
+                negative_cross_attn_mask=None, input_concat_cond=None, global_embed=None, prepend_cond=None,
+                prepend_cond_mask=None, cfg_scale=1.0, cfg_dropout_prob=0.0, causal=False, scale_phi=0.0, mask=None,
+                return_info=False, **kwargs):
+        if causal:
+            raise AssertionError("Causal mode is not supported for DiffusionTransformer")
+        if input_concat_cond is not None or prepend_cond is not None:
+            raise NotImplementedError("input_concat_cond / prepend_cond are not on the native hot path yet")
+        if self.training and cfg_dropout_prob > 0.0:
+            raise NotImplementedError("training-time CFG dropout is outside the inference hot path")
+        if not x.is_cuda:
+            raise _native.NativeError("DiffusionTransformer.forward needs CUDA tensors (no CPU fallback)")
+        # masks are accepted and ignored exactly like the reference (dit.py:250-252,
+        # transformer.py:787-802 never forwards them to the layers)
+        if cross_attn_cond is not None and self.cond_token_dim == 0:
+            cross_attn_cond = None
+        use_cfg = cfg_scale != 1.0 and cross_attn_cond is not None
+        neg = None
+        if use_cfg and negative_cross_attn_cond is not None:
+            neg = negative_cross_attn_cond
+            if negative_cross_attn_mask is not None:
+                neg = torch.where(negative_cross_attn_mask.to(torch.bool).unsqueeze(2), neg, torch.zeros_like(neg))
+                # a fresh tensor every call would defeat the conditioning cache: reuse by content key
+                prev = self.__dict__.get("_neg_masked")
+                if prev is not None and prev[0] == (self._tkey(negative_cross_attn_cond), self._tkey(negative_cross_attn_mask)):
+                    neg = prev[1]
+                else:
+                    self.__dict__["_neg_masked"] = ((self._tkey(negative_cross_attn_cond),
+                                                     self._tkey(negative_cross_attn_mask)), neg)
+        h = self._handle(x.device)
+        B, C, L = x.shape
+        self._prepare(h, cross_attn_cond, neg, global_embed, use_cfg, x.device, B)
+        xin = x.detach().to(torch.float32).contiguous()
+        tin = t.detach().to(torch.float32).contiguous()
+        out = torch.empty_like(xin)
+        st = _native.stream_ptr(x.device)
+        if return_info:
+            P = 0 if self.global_cond_type == "adaLN" else 1
+            rows = (2 * B if use_cfg else B) * (L + P)
+            hidden = torch.empty(rows, self.embed_dim, device=x.device, dtype=torch.float32)
+            _native.check(_native.lib().satb_dit_forward_debug(h, _native.ptr(xin), _native.ptr(tin), _native.ptr(out),
+                                                               _native.ptr(hidden), B, L, float(cfg_scale),
+                                                               float(scale_phi), st))
+            info = {"hidden_states": [hidden.view(-1, L + P, self.embed_dim)]}
+            return out.to(x.dtype), info
+        _native.check(_native.lib().satb_dit_forward(h, _native.ptr(xin), _native.ptr(tin), _native.ptr(out), B, L,
+                                                     float(cfg_scale), float(scale_phi), st))
+        return out.to(x.dtype)
