@@ -1,0 +1,435 @@
+"""Benchmark of the Stable Audio denoising hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): Stable Audio
+Open 1.0 DiT (1.06 B parameters, random init), 47.55 s stereo 44.1 kHz = 1024 latent tokens,
+batch 4 with classifier-free guidance (8 transformer rows), dpmpp-3m-sde sampler, synthetic
+conditioning; one "step" = one sampler iteration = one CFG denoiser call + the sampler update.
+`value` = denoise steps per second summed over all ranks (weak scaling: every rank runs its
+own batch of 4 prompts, sharded like the reference's generate.py:119-120).  Extra keys report
+audio-seconds/s for a full 100-step generation (100 x step time + the measured Oobleck decode).
+
+--impl reference times the reference's CPU path (the oracle port of the same DiT forward, all
+host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "friendly-stable-audio-tools_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "denoise_steps_per_s"
+UNIT = "steps/s"
+SAO_DIT = dict(io_channels=64, embed_dim=1536, depth=24, num_heads=24, cond_token_dim=768, global_cond_dim=1536,
+               project_cond_tokens=False, transformer_type="continuous_transformer")
+SAO_DEC = dict(out_channels=2, channels=128, c_mults=[1, 2, 4, 8, 16], strides=[2, 4, 4, 8, 8], latent_dim=64,
+               use_snake=True, final_tanh=False)
+LATENT_LEN = 1024          # 2097152 samples / 2048
+CTX_LEN = 130              # 128 T5 tokens + seconds_start + seconds_total
+BATCH = 4
+CFG_SCALE = 7.0
+AUDIO_SECONDS = 2097152 / 44100.0
+GEN_STEPS = 100
+SIGMA_MIN, SIGMA_MAX = 0.3, 500.0    # generate.py:135-136
+
+
+def flops_per_step(B):
+    """algorithmic FLOPs of one CFG denoise step (2*B rows, cross-attention counted
+    only on the B conditional rows, the uncond rows' context is null)."""
+    N, D, M, ctx, ffi = LATENT_LEN + 1, 1536, CTX_LEN, 768, 6144
+    self_f = 2 * N * D * 3 * D + 4 * N * N * D + 2 * N * D * D
+    cross_f = 2 * N * D * D + 4 * N * M * D + 2 * N * D * D          # q, core, out (k/v are step-invariant)
+    ff_f = 2 * N * D * 2 * ffi + 2 * N * ffi * D
+    per_row = 24 * (self_f + ff_f) + 2 * N * 64 * D * 2
+    return 2 * B * per_row + B * 24 * cross_f
+
+
+def config_dict(args, extra=None):
+    c = {"workload": "SA-Open-1.0 DiT denoise step, 47.55 s stereo 44.1 kHz (1024 latent tokens + 1 prepend), "
+                     "batch 4 per GPU with CFG 7 (8 rows), dpmpp-3m-sde update, synthetic T5-shaped conditioning",
+         "global_batch": BATCH * args.gpus, "latent_tokens": LATENT_LEN, "context_tokens": CTX_LEN,
+         "parallelism": f"dp{args.gpus}", "l2_policy": "per-step working set (2.1 GB of 16-bit weights) exceeds the 126 MB L2"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# --------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], None, set(), []
+        for ts, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax = float(parts[2])
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "power_w_max": max(power) if power else None, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """CPU path of the reference: the oracle port of DiffusionTransformer.forward (oracle/dit_oracle.py,
+    pinned to the reference modules by tests/golden) on all host threads.  Each 'step' is a bounded
+    sample of the B=4 workload: ONE conditional+unconditional pair (B=1, 2 rows) through a slice of
+    `d` of the 24 identical blocks, scaled by (24/d)*4 to the full step."""
+    from oracle import dit_oracle as do
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # time one block to size the slice
+    probe_cfg = dict(SAO_DIT, depth=1)
+    sd1 = do.make_dit_weights(probe_cfg, seed=0)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 64, LATENT_LEN, generator=g)
+    t = torch.tensor([0.5])
+    c = torch.randn(1, CTX_LEN, 768, generator=g)
+    ge = torch.randn(1, 1536, generator=g)
+    with torch.no_grad():
+        do.dit_forward(sd1, probe_cfg, x, t, c, ge, cfg_scale=CFG_SCALE)
+        t0 = time.time()
+        do.dit_forward(sd1, probe_cfg, x, t, c, ge, cfg_scale=CFG_SCALE)
+        block_s = time.time() - t0
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    d = int(max(1, min(24, budget / max(block_s, 1e-3))))
+    cfg = dict(SAO_DIT, depth=d)
+    sd = do.make_dit_weights(cfg, seed=0)
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t0 = time.time()
+            do.dit_forward(sd, cfg, x, t, c, ge, cfg_scale=CFG_SCALE)
+            if i >= args.warmup:
+                times.append(time.time() - t0)
+    per_sample = sum(times) / len(times)
+    step_s = per_sample * (24.0 / d) * BATCH          # full B=4 step
+    value = 1.0 / step_s
+    sample = (f"1 of the 4 prompts (2 CFG rows) through {d} of 24 blocks per step, fp32, {cores} threads; "
+              f"scaled x{24.0 / d:.2f} (depth) x{BATCH} (batch)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- native arm
+def build_models(device):
+    from oracle import dit_oracle as do
+    from oracle import oobleck_oracle as oo
+    from stable_audio_tools.models.autoencoders import OobleckDecoder
+    from stable_audio_tools.models.diffusion import DiTWrapper
+    wrapper = DiTWrapper(**SAO_DIT)
+    # random-init weights of the SA-Open-1.0 architecture (no checkpoint exists offline); the reference
+    # zero-inits every branch output, which would make the step trivially sparse, so use the
+    # re-randomised synthetic weights of the parity tests.
+    wrapper.model.load_state_dict(do.make_dit_weights(SAO_DIT, seed=0))
+    wrapper = wrapper.to(device).eval()
+    dec = OobleckDecoder(**SAO_DEC)
+    dec.load_state_dict(oo.make_oobleck_weights(oo.decoder_param_shapes(SAO_DEC), seed=1,
+                                                transposed=oo.decoder_transposed_prefixes(SAO_DEC)))
+    dec = dec.to(device).eval()
+    return wrapper, dec
+
+
+def cpu_baseline_leg():
+    """Oracle port of one CFG pair (B=1) through 4 of 24 blocks on all host threads, scaled."""
+    from oracle import dit_oracle as do
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    d = 4
+    cfg = dict(SAO_DIT, depth=d)
+    sd = do.make_dit_weights(cfg, seed=0)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 64, LATENT_LEN, generator=g)
+    t = torch.tensor([0.5])
+    c = torch.randn(1, CTX_LEN, 768, generator=g)
+    ge = torch.randn(1, 1536, generator=g)
+    with torch.no_grad():
+        do.dit_forward(sd, cfg, x, t, c, ge, cfg_scale=CFG_SCALE)
+        n, t0 = 0, time.time()
+        while n < 3 or time.time() - t0 < 8.0:
+            do.dit_forward(sd, cfg, x, t, c, ge, cfg_scale=CFG_SCALE)
+            n += 1
+        per = (time.time() - t0) / n
+    step_s = per * (24.0 / d) * BATCH
+    return {"value": 1.0 / step_s, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} x (1 of 4 prompts, 2 CFG rows, {d} of 24 blocks) fp32 on {cores} threads, "
+                      f"scaled x{24 // d} depth x{BATCH} batch"}
+
+
+def run_native(args):
+    from stable_audio_tools import _native
+    from stable_audio_tools.inference.sampling import VDenoiser, get_sigmas_polyexponential
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = world > 1
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if dist:
+        import torch.distributed as td
+        td.init_process_group("nccl", device_id=device)
+    wrapper, dec = build_models(device)
+    lib = _native.lib()
+
+    # conditioning for the whole job is produced on rank 0 and broadcast once over NCCL (the only
+    # collective of the path); each rank keeps its reference-style shard items[rank::world]
+    n_total = BATCH * world
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    cross_all = torch.randn(n_total, CTX_LEN, 768, generator=g)
+    cross_all[:, 40:128] = 0.0               # padded T5 positions are exact zeros (conditioners.py:343-344)
+    glob_all = torch.randn(n_total, 1536, generator=g)
+    cross_all, glob_all = cross_all.to(device), glob_all.to(device)
+    if dist:
+        if rank != 0:
+            cross_all.zero_()
+            glob_all.zero_()
+        td.broadcast(cross_all, 0)
+        td.broadcast(glob_all, 0)
+    cross = cross_all[rank::world].contiguous()
+    glob = glob_all[rank::world].contiguous()
+    mask = torch.ones(BATCH, CTX_LEN, device=device)
+    cond = dict(cross_attn_cond=cross, cross_attn_mask=mask, global_cond=glob, cfg_scale=CFG_SCALE, batch_cfg=True,
+                rescale_cfg=True)
+
+    denoiser = VDenoiser(wrapper)
+    sigmas = get_sigmas_polyexponential(GEN_STEPS, SIGMA_MIN, SIGMA_MAX, 1.0, device=device)
+    sig = [float(s) for s in sigmas]
+    torch.manual_seed(100 + rank)
+    x0 = torch.randn(BATCH, 64, LATENT_LEN, device=device) * sigmas[0]
+    ones = torch.ones(BATCH, device=device)
+    import math
+
+    class Loop:
+        """dpmpp-3m-sde state machine, one model call per step (restated k-diffusion, see sampling.py)."""
+
+        def __init__(self):
+            self.x = x0.clone()
+            self.i = 0
+            self.d1 = self.d2 = None
+            self.h1 = self.h2 = None
+
+        def step(self, x_in=None):
+            i = self.i % (GEN_STEPS - 1)      # stay inside the non-terminal part of the schedule
+            x = self.x if x_in is None else x_in
+            den = denoiser(x, sigmas[i] * ones, **cond)
+            h = math.log(sig[i]) - math.log(sig[i + 1])
+            h_eta = 2 * h
+            xn = math.exp(-h_eta) * x + (-math.expm1(-h_eta)) * den
+            if self.h2 is not None:
+                r0, r1 = self.h1 / h, self.h2 / h
+                d1_0 = (den - self.d1) / r0
+                d1_1 = (self.d1 - self.d2) / r1
+                d1 = d1_0 + (d1_0 - d1_1) * (r0 / (r0 + r1))
+                dd2 = (d1_0 - d1_1) / (r0 + r1)
+                phi_2 = math.expm1(-h_eta) / h_eta + 1
+                phi_3 = phi_2 / h_eta - 0.5
+                xn = xn + phi_2 * d1 - phi_3 * dd2
+            elif self.h1 is not None:
+                phi_2 = math.expm1(-h_eta) / h_eta + 1
+                xn = xn + phi_2 * ((den - self.d1) / (self.h1 / h))
+            xn = xn + torch.randn_like(x) * (sig[i + 1] * math.sqrt(-math.expm1(-2 * h)))
+            self.d1, self.d2 = den, self.d1
+            self.h1, self.h2 = h, self.h1
+            self.x = xn
+            self.i += 1
+            return xn
+
+    def barrier():
+        if dist:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    loop = Loop()
+    for _ in range(max(args.warmup, 3)):
+        loop.step()
+    h_dit = wrapper.model._handle(device)
+
+    # ---------------- timed region: K steps, inputs resident in HBM -------------------------
+    _native.check(lib.satb_dit_profile(h_dit, 1))
+    ms8, cnt8 = (ctypes.c_float * 8)(), (ctypes.c_int * 8)()
+    _native.check(lib.satb_dit_profile_read(h_dit, ms8, cnt8))   # clear
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    launches0 = _native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        loop.step()
+    e1.record()
+    barrier()
+    wall1 = time.time()
+    launches = _native.launch_count() - launches0
+    elapsed_ms = e0.elapsed_time(e1)
+    _native.check(lib.satb_dit_profile_read(h_dit, ms8, cnt8))
+    _native.check(lib.satb_dit_profile(h_dit, 0))
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    if dist:
+        tmax = torch.tensor([elapsed_ms], device=device)
+        td.all_reduce(tmax, op=td.ReduceOp.MAX)
+        elapsed_ms = float(tmax.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * args.steps / (elapsed_ms / 1e3)
+
+    # ---------------- e2e: same steps through the public call with HOST buffers --------------
+    x_host = torch.empty(BATCH, 64, LATENT_LEN, pin_memory=True).copy_(loop.x.cpu())
+    out_host = torch.empty(BATCH, 64, LATENT_LEN, pin_memory=True)
+    x_dev = torch.empty(BATCH, 64, LATENT_LEN, device=device)
+    loop2 = Loop()
+    loop2.d1, loop2.d2, loop2.h1, loop2.h2, loop2.i = loop.d1, loop.d2, loop.h1, loop.h2, loop.i
+    for _ in range(2):
+        x_dev.copy_(x_host, non_blocking=True)
+        out_host.copy_(loop2.step(x_dev), non_blocking=True)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        x_dev.copy_(x_host, non_blocking=True)                  # H2D of this step's input latents
+        out_host.copy_(loop2.step(x_dev), non_blocking=True)    # D2H of this step's result
+    e3.record()
+    barrier()
+    e2e_ms = e2.elapsed_time(e3)
+    if dist:
+        tmax = torch.tensor([e2e_ms], device=device)
+        td.all_reduce(tmax, op=td.ReduceOp.MAX)
+        e2e_ms = float(tmax.item())
+    e2e_value = world * args.steps / (e2e_ms / 1e3)
+    io_bytes = BATCH * 64 * LATENT_LEN * 4
+
+    # ---------------- Oobleck decode of the batch (audio-seconds/s of a full generation) ------
+    lat = loop.x / max(float(loop.x.abs().max()), 1.0)
+    audio = dec(lat[:1])
+    barrier()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for b in range(BATCH):                       # one item at a time, like the reference's iterate_batch
+        audio = dec(lat[b:b + 1])
+    d1.record()
+    torch.cuda.synchronize()
+    decode_ms = d0.elapsed_time(d1)
+    if dist:
+        tmax = torch.tensor([decode_ms], device=device)
+        td.all_reduce(tmax, op=td.ReduceOp.MAX)
+        decode_ms = float(tmax.item())
+    gen_ms = GEN_STEPS * ms_per_step + decode_ms
+    audio_sec_per_s = world * BATCH * AUDIO_SECONDS / (gen_ms / 1e3)
+
+    if rank != 0:
+        if dist:
+            td.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (FF-in GEMM, tensor bound) --------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained, kernel timed inside a long step)" \
+        if "bf16_tflops_sustained" in peaks else "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
+    M = 2 * BATCH * (LATENT_LEN + 1)
+    ff_in_flops = 2.0 * M * 12288 * 1536
+    ff_in_ms = ms8[0] / max(cnt8[0], 1)
+    achieved = ff_in_flops / (ff_in_ms / 1e3) / 1e12 if ff_in_ms > 0 else None
+    cats = ["ff_in_gemm", "ff_out_gemm", "qkv_gemm", "self_attention", "attn_out_gemm", "cross_attention", "layernorm"]
+    breakdown = {c: {"ms_per_step": ms8[i] / args.steps, "launch_groups": cnt8[i] // args.steps} for i, c in enumerate(cats)}
+    step_tflops = flops_per_step(BATCH) / (ms_per_step / 1e3) / 1e12
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16 operands, fp32 accumulate (the reference's autocast dtype)", "data": "synthetic",
+        "config": config_dict(args),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<EpiSwiglu> (FF-in 8200x12288x1536)",
+                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": (achieved / peak_tf) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "avg_launch_ms": ff_in_ms},
+        "step_tflops": step_tflops, "step_frac_of_peak": step_tflops / peak_tf,
+        "kernel_breakdown": breakdown,
+        "decode_ms_batch": decode_ms, "audio_sec_per_s_100step": audio_sec_per_s,
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_leg()
+    print(json.dumps(line), flush=True)
+    if dist:
+        td.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            args.no_cpu_baseline = True     # the CPU baseline is reported at N=1 only
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

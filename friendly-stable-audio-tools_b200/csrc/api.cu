@@ -27,7 +27,7 @@ int satb_linear_f32out(const void* a16, const void* w16, float* c, int M, int N,
   CUtensorMap ta, tb;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GemmShape s;
-  s.L = M; s.batches = 1; s.N = N; s.K = K; s.n_taps = 1; s.tap_base = 0; s.tap_step = 0; s.b_tap_rows = N;
+  s.L = M; s.batches = 1; s.N = N; s.K = K; s.n_taps = 1; s.tap_base = 0; s.tap_step = 0; s.b_tap_rows = N; s.stride = 1;
   EpiStore32::Params ep{c, N, nullptr};
   SATB_PROPAGATE(make_tmap_a(&ta, a16, K, M, 1, K, static_cast<int64_t>(M) * K));
   if (N % 256 == 0 || N > 256) {

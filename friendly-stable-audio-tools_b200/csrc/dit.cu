@@ -79,7 +79,7 @@ static int linear(TmapCache& tc, const void* A, int64_t lda, int M, int K, const
   SATB_PROPAGATE(tc.get_a(A, K, M, 1, lda, static_cast<int64_t>(M) * lda, &ta));
   SATB_PROPAGATE(tc.get_b(W, K, N, K, BN, &tb));
   GemmShape s;
-  s.L = M; s.batches = 1; s.N = N; s.K = K; s.n_taps = 1; s.tap_base = 0; s.tap_step = 0; s.b_tap_rows = N;
+  s.L = M; s.batches = 1; s.N = N; s.K = K; s.n_taps = 1; s.tap_base = 0; s.tap_step = 0; s.b_tap_rows = N; s.stride = 1;
   return launch_gemm<Epi, BN, BF16>(*ta, *tb, s, ep, stream);
 }
 
@@ -119,6 +119,15 @@ struct SatbDit {
   DevBuf ws_h, ws_a16, ws_qkv, ws_attn, ws_q16, ws_ff, ws_ain, ws_y, ws_small, ws_cond, ws_kv, ws_rope;
   int rope_len = 0;
   int res_R = 0, res_L = 0;
+  // optional per-category CUDA-event timing (bench.py roofline)
+  bool prof_on = false;
+  struct ProfRec { int cat; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  cudaEvent_t prof_event() {
+    if (!prof_pool.empty()) { cudaEvent_t e = prof_pool.back(); prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
 
   template <class T>
   int alloc(T** p, size_t n) {
@@ -463,6 +472,18 @@ int satb_dit_prepare_cond(SatbDit* d, const float* cross, const float* neg_cross
 
 }  // extern "C"
 
+// RAII helper: records a start/stop event pair around a kernel sequence when profiling is on
+struct ProfScope {
+  SatbDit* d; int cat; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(SatbDit* d_, int cat_, cudaStream_t st_) : d(d_), cat(cat_), st(st_) {
+    if (d->prof_on) { a = d->prof_event(); b = d->prof_event(); cudaEventRecord(a, st); }
+  }
+  ~ProfScope() {
+    if (a) { cudaEventRecord(b, st); d->prof_recs.push_back({cat, a, b}); }
+  }
+};
+enum { PROF_FF_IN = 0, PROF_FF_OUT, PROF_QKV, PROF_ATTN_SELF, PROF_ATTN_OUT, PROF_CROSS, PROF_LN, PROF_OTHER, PROF_NCAT };
+
 template <bool BF16>
 static int dit_forward_impl(SatbDit* d, const float* x, const float* t, float* out, int B, int L, float cfg_scale,
                             float scale_phi, cudaStream_t st, float* hidden_out) {
@@ -503,22 +524,31 @@ static int dit_forward_impl(SatbDit* d, const float* x, const float* t, float* o
     const LayerW& W = d->layers[i];
     const float* ssg_l = d->adaln ? sw.ssg + static_cast<size_t>(i) * 6 * D : nullptr;
     // ---- self-attention: LN -> QKV GEMM (+RoPE) -> attention -> out-proj (+residual)
-    SATB_PROPAGATE(launch_layernorm(h, W.pre_g, W.pre_b, a16, M, D, ssg_l, ssg_l ? ssg_l + D : nullptr, ssg_ld, N_seq, B, BF16, st));
     {
+      ProfScope ps(d, PROF_LN, st);
+      SATB_PROPAGATE(launch_layernorm(h, W.pre_g, W.pre_b, a16, M, D, ssg_l, ssg_l ? ssg_l + D : nullptr, ssg_ld, N_seq, B, BF16, st));
+    }
+    {
+      ProfScope ps(d, PROF_QKV, st);
       typedef EpiQkvRope<BF16> E;
       typename E::Params ep{qkv, 3 * D, 2 * D, N_seq, cos_tab, sin_tab};
       SATB_PROPAGATE((linear<E, 256, BF16>(d->tmaps, a16, D, M, D, W.w_qkv, 3 * D, ep, st)));
     }
-    SATB_PROPAGATE(launch_attention(qkv, qkv + D, qkv + 2 * D, att, 3 * D, 3 * D, 3 * D, D,
-                                    static_cast<int64_t>(N_seq) * 3 * D, static_cast<int64_t>(N_seq) * 3 * D,
-                                    static_cast<int64_t>(N_seq) * 3 * D, static_cast<int64_t>(N_seq) * D, R, H, H, N_seq,
-                                    N_seq, d->dh, BF16, st));
     {
+      ProfScope ps(d, PROF_ATTN_SELF, st);
+      SATB_PROPAGATE(launch_attention(qkv, qkv + D, qkv + 2 * D, att, 3 * D, 3 * D, 3 * D, D,
+                                      static_cast<int64_t>(N_seq) * 3 * D, static_cast<int64_t>(N_seq) * 3 * D,
+                                      static_cast<int64_t>(N_seq) * 3 * D, static_cast<int64_t>(N_seq) * D, R, H, H, N_seq,
+                                      N_seq, d->dh, BF16, st));
+    }
+    {
+      ProfScope ps(d, PROF_ATTN_OUT, st);
       EpiResidual::Params ep{h, D, nullptr, ssg_l ? ssg_l + 2 * D : nullptr, N_seq, static_cast<int>(ssg_ld), B};
       SATB_PROPAGATE((linear<EpiResidual, 256, BF16>(d->tmaps, att, D, M, D, W.w_o, D, ep, st)));
     }
     // ---- cross-attention on the rows that have a non-null context
     if (Mc > 0) {
+      ProfScope ps(d, PROF_CROSS, st);
       const int Hkv = d->ce / 64;
       SATB_PROPAGATE(launch_layernorm(h, W.ca_g, W.ca_b, a16, Mc, D, nullptr, nullptr, 0, N_seq, 1, BF16, st));
       {
@@ -537,14 +567,19 @@ static int dit_forward_impl(SatbDit* d, const float* x, const float* t, float* o
       }
     }
     // ---- feed-forward: LN -> GEMM (+bias, SwiGLU) -> GEMM (+bias, +residual)
-    SATB_PROPAGATE(launch_layernorm(h, W.ff_g, W.ff_b, a16, M, D, ssg_l ? ssg_l + 3 * D : nullptr,
-                                    ssg_l ? ssg_l + 4 * D : nullptr, ssg_ld, N_seq, B, BF16, st));
     {
+      ProfScope ps(d, PROF_LN, st);
+      SATB_PROPAGATE(launch_layernorm(h, W.ff_g, W.ff_b, a16, M, D, ssg_l ? ssg_l + 3 * D : nullptr,
+                                      ssg_l ? ssg_l + 4 * D : nullptr, ssg_ld, N_seq, B, BF16, st));
+    }
+    {
+      ProfScope ps(d, PROF_FF_IN, st);
       typedef EpiSwiglu<BF16> E;
       typename E::Params ep{ff, d->ffi, W.b_ff1};
       SATB_PROPAGATE((linear<E, 256, BF16>(d->tmaps, a16, D, M, D, W.w_ff1, 2 * d->ffi, ep, st)));
     }
     {
+      ProfScope ps(d, PROF_FF_OUT, st);
       EpiResidual::Params ep{h, D, W.b_ff2, ssg_l ? ssg_l + 5 * D : nullptr, N_seq, static_cast<int>(ssg_ld), B};
       SATB_PROPAGATE((linear<EpiResidual, 256, BF16>(d->tmaps, ff, d->ffi, M, d->ffi, W.w_ff2, D, ep, st)));
     }
@@ -572,6 +607,31 @@ int satb_dit_forward(SatbDit* d, const float* x, const float* t, float* out, int
   cudaStream_t st = static_cast<cudaStream_t>(stream_v);
   return d->bf16 ? dit_forward_impl<true>(d, x, t, out, B, L, cfg_scale, scale_phi, st, nullptr)
                  : dit_forward_impl<false>(d, x, t, out, B, L, cfg_scale, scale_phi, st, nullptr);
+}
+
+// Per-category kernel timing with CUDA events on the launching stream (bench.py roofline):
+// categories 0 ff_in GEMM, 1 ff_out GEMM, 2 qkv GEMM, 3 self-attention core, 4 attn out GEMM,
+// 5 cross-attention (LN + q GEMM + core + out GEMM), 6 LayerNorm.
+int satb_dit_profile(SatbDit* d, int enable) {
+  SATB_REQUIRE(d, "null handle");
+  d->prof_on = enable != 0;
+  return 0;
+}
+// Synchronises, sums the recorded intervals per category into ms[8] / count[8], and clears them.
+int satb_dit_profile_read(SatbDit* d, float* ms, int* count) {
+  SATB_REQUIRE(d && ms && count, "null argument");
+  for (int i = 0; i < PROF_NCAT; ++i) { ms[i] = 0.f; count[i] = 0; }
+  for (auto& r : d->prof_recs) {
+    SATB_CHECK_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    SATB_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.cat] += t;
+    count[r.cat] += 1;
+    d->prof_pool.push_back(r.a);
+    d->prof_pool.push_back(r.b);
+  }
+  d->prof_recs.clear();
+  return 0;
 }
 
 // Debug/test variant that also returns the residual stream after the last block

@@ -2,9 +2,9 @@
 //
 //   C[row, n] = sum_{tap, k} A[batch, l + tap_base + tap*tap_step, k] * B[tap*b_tap_rows + n, k]
 //
-// A is a K-major 16-bit activation matrix viewed as (K, L, batches) through a
-// 3-D TMA tensor map (out-of-range rows are zero-filled by TMA, which is how
-// dilated-convolution padding and the ragged M tail are handled); B is the
+// A is a K-major 16-bit activation matrix viewed as (K, phase, L, batches) through a
+// 4-D TMA tensor map (position = row*stride + phase; out-of-range rows are zero-filled
+// by TMA, which is how convolution padding and the ragged M tail are handled); B is the
 // K-major weight matrix [taps * N, K].  A plain Linear layer is n_taps = 1,
 // batches = 1.  Accumulation is fp32 in TMEM.
 //
@@ -26,9 +26,11 @@ struct GemmShape {
   int N;            // output columns
   int K;            // reduction length per tap (multiple of 8)
   int n_taps;       // 1 for Linear, 7 for conv k7, 2 for transposed conv phases
-  int tap_base;     // row offset of tap 0 (e.g. -3*dilation)
-  int tap_step;     // row offset increment per tap (dilation; -1 for transposed conv)
-  int b_tap_rows;   // rows of B per tap (= N padded as stored)
+  int tap_base;     // position offset of tap 0 (e.g. -3*dilation, or -padding)
+  int tap_step;     // position offset increment per tap (dilation; -1 for transposed conv)
+  int b_tap_rows;   // rows of B per tap (= N as stored)
+  int stride;       // >1: strided conv; tap position u = l*stride + tap_base + tap*tap_step is
+                    // addressed as (phase = u mod stride, row = u div stride) of the 4-D map
 };
 
 constexpr int kBlockM = 128;
@@ -120,7 +122,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint8_t* sa = smem + stage * Cfg::kStage;
           uint8_t* sb = sa + Cfg::kStageA;
           mbar_expect_tx(&full_bar[stage], Cfg::kStage);
-          tma_load_3d(sa, &tmA, &full_bar[stage], k0, m0 + s.tap_base + tap * s.tap_step, batch);
+          const int u = s.tap_base + tap * s.tap_step;
+          int ph = 0, ro = u;
+          if (s.stride > 1) {
+            ro = (u >= 0) ? u / s.stride : -((-u + s.stride - 1) / s.stride);   // floor division
+            ph = u - ro * s.stride;
+          }
+          tma_load_4d(sa, &tmA, &full_bar[stage], k0, ph, m0 + ro, batch);
           tma_load_2d(sb, &tmB, &full_bar[stage], k0, tap * s.b_tap_rows + n0);
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -394,9 +402,117 @@ struct EpiSwiglu {
   }
 };
 
+// ------------------------------------------------------- convolution epilogues
+// SnakeBeta (models/blocks.py:318-319) with precomputed a = e^alpha, ib = 1/(e^beta + 1e-9).
+// sin^2 has period pi: reduce the argument to [-pi/2, pi/2] (two-constant Cody-Waite) and
+// use the SFU sine there (abs error ~2^-21, far below the 16-bit operand rounding that follows).
+__device__ __forceinline__ float snake_fast(float v, float a, float ib) {
+  const float th = v * a;
+  const float k = rintf(th * 0.318309886183790672f);
+  float r = fmaf(-k, 3.14159274101257324f, th);
+  r = fmaf(-k, -8.74227765734758577e-8f, r);
+  const float sn = __sinf(r);
+  return fmaf(ib, sn * sn, v);
+}
+
+// Epilogue of every tensor-core convolution of the Oobleck VAE (models/autoencoders.py:45-116):
+//   y = acc + bias[co] (+ resid[pos, co])            ResidualUnit skip :66-68
+//   raw_out[pos, co] = y (fp32, optional)            kept only where a later skip needs it
+//   s16_out[pos, co] = 16-bit( snake_next(y) )       the NEXT layer's activation, fused here
+// Transposed convolutions (:102-105) run as a 2-tap GEMM over N = up*cout columns
+// (column = phase*cout + co): output position = l*up + phase - pad.
+template <bool BF16>
+struct EpiConv {
+  static constexpr int kCols = 32;
+  struct Params {
+    const float* bias;    // [cout] or null
+    const float* resid;   // fp32 [B*L_out, cout] or null
+    float* raw_out;       // fp32 [B*L_out, cout] or null
+    void* s16_out;        // 16-bit [B*L_out, cout] or null
+    const float* sn_a;    // [cout] e^alpha of the consumer's Snake, or null (plain cast)
+    const float* sn_ib;   // [cout] 1/(e^beta + 1e-9)
+    int cout;
+    int L_out;            // output positions per batch item
+    int up;               // transposed-conv stride (1 = ordinary conv)
+    int pad;              // transposed-conv padding
+  };
+  __device__ static __forceinline__ void apply(const Params& p, const EpiCtx& c, const uint32_t (&r)[32]) {
+    if (!c.valid) return;
+    int phase = 0, co0 = c.col0;
+    if (p.up > 1) {
+      phase = c.col0 / p.cout;
+      co0 = c.col0 - phase * p.cout;
+    }
+    const int lo = c.l * p.up + phase - p.pad;
+    if (lo < 0 || lo >= p.L_out) return;
+    const size_t base = (static_cast<size_t>(c.batch) * p.L_out + lo) * p.cout + co0;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0) + j);
+        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      }
+    }
+    if (p.resid) {
+      const float4* rs = reinterpret_cast<const float4*>(p.resid + base);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = rs[j];
+        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      }
+    }
+    if (p.raw_out) {
+      float4* ro = reinterpret_cast<float4*>(p.raw_out + base);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ro[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    if (p.s16_out) {
+      if (p.sn_a) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(p.sn_a + co0) + j);
+          const float4 ib = __ldg(reinterpret_cast<const float4*>(p.sn_ib + co0) + j);
+          v[4 * j] = snake_fast(v[4 * j], a.x, ib.x);
+          v[4 * j + 1] = snake_fast(v[4 * j + 1], a.y, ib.y);
+          v[4 * j + 2] = snake_fast(v[4 * j + 2], a.z, ib.z);
+          v[4 * j + 3] = snake_fast(v[4 * j + 3], a.w, ib.w);
+        }
+      }
+      uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.s16_out) + base);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        dst[j] = make_uint4(Op16<BF16>::pack(v[8 * j], v[8 * j + 1]), Op16<BF16>::pack(v[8 * j + 2], v[8 * j + 3]),
+                            Op16<BF16>::pack(v[8 * j + 4], v[8 * j + 5]), Op16<BF16>::pack(v[8 * j + 6], v[8 * j + 7]));
+    }
+  }
+};
+
+// out[b, n, l] (NCL fp32) = acc + bias[n]; consecutive lanes hold consecutive l, so every
+// per-column store is a coalesced 128 B line.
+struct EpiStoreNCL {
+  static constexpr int kCols = 32;
+  struct Params {
+    float* out;
+    const float* bias;
+    int N;
+    int L;
+  };
+  __device__ static __forceinline__ void apply(const Params& p, const EpiCtx& c, const uint32_t (&r)[32]) {
+    if (!c.valid) return;
+    float* o = p.out + (static_cast<size_t>(c.batch) * p.N + c.col0) * p.L + c.l;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (c.col0 + j < p.N) o[static_cast<size_t>(j) * p.L] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + c.col0 + j) : 0.f);
+    }
+  }
+};
+
 // ------------------------------------------------------------------ host side
 int make_tmap_a(CUtensorMap* m, const void* ptr, int K, int L, int batches, int64_t row_stride_elems,
-                int64_t batch_stride_elems);
+                int64_t batch_stride_elems, int stride = 1);
 int make_tmap_b(CUtensorMap* m, const void* ptr, int K, int rows, int64_t row_stride_elems, int box_rows);
 
 template <class Epi, int BN, bool BF16>

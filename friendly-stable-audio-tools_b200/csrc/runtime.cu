@@ -42,18 +42,23 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// A operand: 16-bit, dims (K, L, batches), box (64, 128, 1), 128B swizzle, zero OOB fill.
+// A operand: 16-bit, dims (K, phase, rows, batches) with position = row*stride + phase
+// (stride 1 for everything but strided convolutions), box (64, 1, 128, 1), 128B swizzle,
+// zero OOB fill.  L = number of rows (positions / stride).
 int make_tmap_a(CUtensorMap* m, const void* ptr, int K, int L, int batches, int64_t row_stride_elems,
-                int64_t batch_stride_elems) {
+                int64_t batch_stride_elems, int stride) {
   EncodeTiledFn fn = get_encode_fn();
   SATB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
   SATB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base must be 16B aligned");
   SATB_REQUIRE((row_stride_elems * 2) % 16 == 0 && (batch_stride_elems * 2) % 16 == 0, "TMA strides must be 16B multiples");
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(batches)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_stride_elems) * 2, static_cast<cuuint64_t>(batch_stride_elems) * 2};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(kBlockM), 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(stride), static_cast<cuuint64_t>(L),
+                        static_cast<cuuint64_t>(batches)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(row_stride_elems) * 2,
+                           static_cast<cuuint64_t>(row_stride_elems) * 2 * stride,
+                           static_cast<cuuint64_t>(batch_stride_elems) * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(kBlockK), 1, static_cast<cuuint32_t>(kBlockM), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

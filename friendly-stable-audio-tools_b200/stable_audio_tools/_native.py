@@ -51,6 +51,8 @@ SIGNATURES = {
     "satb_dit_prepare_cond": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "satb_dit_forward": (_I, [_VP, _VP, _VP, _VP, _I, _I, _F, _F, _VP]),
     "satb_dit_forward_debug": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _F, _F, _VP]),
+    "satb_dit_profile": (_I, [_VP, _I]),
+    "satb_dit_profile_read": (_I, [_VP, _VP, _VP]),
     "satb_snake_beta": (_I, [_VP, _VP, _VP, _VP, _I, _I, _LL, _I, _VP]),
     "satb_layernorm": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "satb_linear_f32out": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP]),

@@ -86,6 +86,12 @@ int satb_dit_forward(SatbDit* h, const float* x, const float* t, float* out, int
 int satb_dit_forward_debug(SatbDit* h, const float* x, const float* t, float* out, float* hidden, int B, int L,
                            float cfg_scale, float scale_phi, void* stream);
 
+/* Per-kernel-class CUDA-event timing used by bench.py's roofline line: enable, run forwards,
+ * then read ms[8]/count[8] (0 ff_in GEMM, 1 ff_out GEMM, 2 qkv GEMM, 3 self-attention core,
+ * 4 attention out GEMM, 5 cross-attention, 6 LayerNorm, 7 unused). */
+int satb_dit_profile(SatbDit* h, int enable);
+int satb_dit_profile_read(SatbDit* h, float* ms, int* count);
+
 /* ---- primitives exposed for the drop-in modules and the parity tests ---------------- */
 /* SnakeBeta.forward (models/blocks.py:330-358): x, y [B, C, T]; alpha, beta [C]. */
 int satb_snake_beta(const float* x, const float* alpha, const float* beta, float* y, int B, int C, long long T,

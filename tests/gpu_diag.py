@@ -135,6 +135,73 @@ def dit_full(depth, B, cfg_scale):
     return f
 
 
+def oobleck_golden(dtype="fp16"):
+    def f():
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import test_gpu_oobleck as tg
+        g, ae = tg._build(dtype)
+        y = ae.decoder(torch.from_numpy(g["z"]).cuda()).cpu()
+        h = ae.encoder(torch.from_numpy(g["a"]).cuda()).cpu()
+        return dict(dec=rel_l2(y, torch.from_numpy(g["audio"])), enc=rel_l2(h, torch.from_numpy(g["h"])))
+    return f
+
+
+def oobleck_full(L):
+    def f():
+        from oracle import oobleck_oracle as oo
+        from stable_audio_tools.models.autoencoders import OobleckDecoder
+        dcfg = dict(out_channels=2, channels=128, c_mults=[1, 2, 4, 8, 16], strides=[2, 4, 4, 8, 8], latent_dim=64,
+                    use_snake=True, final_tanh=False)
+        dsd = oo.make_oobleck_weights(oo.decoder_param_shapes(dcfg), seed=9, transposed=oo.decoder_transposed_prefixes(dcfg))
+        dec = OobleckDecoder(**dcfg)
+        dec.load_state_dict(dsd)
+        dec = dec.cuda().eval()
+        torch.manual_seed(3)
+        z = torch.randn(1, 64, L)
+        out = {}
+        if L <= 32:
+            t0 = time.time()
+            ref = oo.oobleck_decoder(z, dsd, dcfg)
+            out["cpu_s"] = time.time() - t0
+            y = dec(z.cuda())
+            out["rel"] = rel_l2(y.cpu(), ref)
+        zc = z.cuda()
+        y = dec(zc)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            y = dec(zc)
+        e1.record(); torch.cuda.synchronize()
+        out["gpu_ms"] = e0.elapsed_time(e1) / 3
+        out["finite"] = bool(torch.isfinite(y).all())
+        return out
+    return f
+
+
+def dit_timing(B, depth=24):
+    def f():
+        from oracle import dit_oracle as do
+        cfg = dict(SAO_DIT, depth=depth)
+        sd = do.make_dit_weights(cfg, seed=5)
+        m = build_native_dit(cfg, sd)
+        torch.manual_seed(1)
+        x = torch.randn(B, 64, 1024).cuda(); t = (torch.rand(B) * 0.9 + 0.05).cuda()
+        c = torch.randn(B, 130, 768).cuda(); ge = torch.randn(B, 1536).cuda()
+        for _ in range(3):
+            y = m(x, t, cross_attn_cond=c, global_embed=ge, cfg_scale=7.0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            y = m(x, t, cross_attn_cond=c, global_embed=ge, cfg_scale=7.0)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        tf = 2.272e12 * 2 * B * depth / 24
+        return dict(ms=ms, tflops=tf / ms / 1e9, finite=bool(torch.isfinite(y).all()))
+    return f
+
+
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), os.cpu_count(), "cpus", flush=True)
     run("snake", snake_case)
@@ -150,6 +217,13 @@ if __name__ == "__main__":
     run("dit_prepend_small_bf16", dit_golden("dit_prepend_small.npz", "bf16"))
     run("dit_full_d2_cfg", dit_full(2, 1, 7.0))
     run("dit_full_d1_nocfg", dit_full(1, 2, 1.0))
+    run("oobleck_small_fp16", oobleck_golden("fp16"))
+    run("oobleck_small_bf16", oobleck_golden("bf16"))
+    run("oobleck_full_L8", oobleck_full(8))
+    run("oobleck_full_L32", oobleck_full(32))
+    run("oobleck_full_L1024", oobleck_full(1024))
+    run("dit_timing_B1", dit_timing(1))
+    run("dit_timing_B4", dit_timing(4))
     print("\n==== SUMMARY ====")
     for r in results:
         print(r)
