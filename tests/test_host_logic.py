@@ -1,0 +1,189 @@
+"""CPU: host-side logic of the drop-in package (no kernels): sampler arithmetic, sigma schedule,
+conditioning routing, chunk / cross-fade orchestration, rank sharding, gloo world_size-2 path."""
+import math
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from helpers import rel_l2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_sigma_schedule_and_vdenoiser_scalings():
+    from stable_audio_tools.inference.sampling import VDenoiser, get_sigmas_polyexponential
+    s = get_sigmas_polyexponential(100, 0.3, 500.0, 1.0)
+    assert s.shape == (101,) and s[-1] == 0
+    assert abs(float(s[0]) - 500.0) < 1e-3 and abs(float(s[99]) - 0.3) < 1e-6
+    assert bool((s[:-1][1:] < s[:-1][:-1]).all())
+    # log-linear for rho = 1
+    r = torch.log(s[:100])
+    assert float((r[1:] - r[:-1]).std()) < 1e-5
+    seen = {}
+
+    def inner(x, t, **kw):
+        seen["x"], seen["t"] = x, t
+        return torch.zeros_like(x)
+
+    d = VDenoiser(inner)
+    x = torch.randn(2, 3, 5)
+    sig = torch.tensor([2.0, 0.5])
+    out = d(x, sig)
+    c_in = 1 / (sig ** 2 + 1).sqrt()
+    assert torch.allclose(seen["x"], x * c_in[:, None, None])
+    assert torch.allclose(seen["t"], sig.atan() * 2 / math.pi)
+    assert torch.allclose(out, x / (sig ** 2 + 1)[:, None, None])
+
+
+@pytest.mark.parametrize("name", ["dpmpp-2m-sde", "dpmpp-3m-sde"])
+def test_dropin_samplers_match_oracle_samplers(name):
+    """Host-scalar implementation (no device syncs in the loop) == tensor-arithmetic restatement."""
+    from oracle import sampler_oracle as so
+    from stable_audio_tools.inference import sampling as mine
+    torch.manual_seed(0)
+    w = torch.randn(4, 4) * 0.2
+
+    def toy(x, t, **kw):
+        return torch.einsum("ij,bjl->bil", w, x) * (1 + t[:, None, None])
+
+    seq = [torch.randn(2, 4, 16) for _ in range(12)]
+
+    def ns():
+        it = iter(seq)
+        return lambda a, b: next(it)
+
+    sig = mine.get_sigmas_polyexponential(12, 0.3, 80.0)
+    x0 = torch.randn(2, 4, 16) * sig[0]
+    fn_m = mine.SAMPLERS[name]
+    fn_o = so.sample_dpmpp_2m_sde if "2m" in name else so.sample_dpmpp_3m_sde
+    a = fn_m(mine.VDenoiser(toy), x0.clone(), sig, noise_sampler=ns())
+    b = fn_o(so.VDenoiser(toy), x0.clone(), sig, noise_sampler=ns())
+    assert rel_l2(a, b) < 1e-5
+
+
+def test_sample_k_initialisation_modes():
+    from stable_audio_tools.inference.sampling import sample_k
+    calls = []
+
+    def toy(x, t, **kw):
+        calls.append(kw)
+        return torch.zeros_like(x)
+
+    noise = torch.ones(1, 2, 8)
+    out = sample_k(toy, noise, steps=3, sampler_type="dpmpp-3m-sde", sigma_min=0.5, sigma_max=10, device="cpu",
+                   noise_sampler=lambda a, b: torch.zeros(1, 2, 8), cfg_scale=3.0, cross_attn_cond=None)
+    assert len(calls) == 3 and calls[0]["cfg_scale"] == 3.0
+    assert torch.isfinite(out).all()
+    with pytest.raises(NotImplementedError):
+        sample_k(toy, noise, steps=3, sampler_type="k-heun", device="cpu")
+
+
+def test_get_conditioning_inputs_routing():
+    from stable_audio_tools.models.diffusion import ConditionedDiffusionModelWrapper
+    w = ConditionedDiffusionModelWrapper(torch.nn.Identity(), None, io_channels=64, sample_rate=44100, min_input_length=2048,
+                                         cross_attn_cond_ids=["prompt", "seconds_start", "seconds_total"],
+                                         global_cond_ids=["seconds_start", "seconds_total"])
+    B = 2
+    cond = {"prompt": (torch.randn(B, 128, 768), torch.ones(B, 128)),
+            "seconds_start": (torch.randn(B, 1, 768), torch.ones(B, 1)),
+            "seconds_total": (torch.randn(B, 1, 768), torch.ones(B, 1))}
+    out = w.get_conditioning_inputs(cond)
+    assert out["cross_attn_cond"].shape == (B, 130, 768) and out["cross_attn_mask"].shape == (B, 130)
+    assert out["global_cond"].shape == (B, 1536)
+    assert torch.equal(out["cross_attn_cond"][:, 128], cond["seconds_start"][0][:, 0])
+    neg = w.get_conditioning_inputs(cond, negative=True)
+    assert set(neg) == {"negative_cross_attn_cond", "negative_cross_attn_mask", "negative_global_cond",
+                        "negative_input_concat_cond"}
+
+
+class _FakeEnc(torch.nn.Module):
+    """average-pool 'encoder' (ratio 4, 2 -> 3 channels) so the chunking logic runs on CPU"""
+
+    def forward(self, x):
+        p = torch.nn.functional.avg_pool1d(x, 4)
+        return torch.cat([p, p[:, :1] * 0.5 - 3.0], dim=1)
+
+
+class _FakeDec(torch.nn.Module):
+    def forward(self, z):
+        return torch.repeat_interleave(z[:, :2] + z[:, 2:3] * 0.25, 4, dim=-1)
+
+
+def test_chunked_encode_decode_reconstruct_match_reference_or_closed_form():
+    """With linear, position-wise fake encoder/decoder the Bartlett cross-fade weights sum to one on
+    the overlaps, so chunked == unchunked away from the padded tail; when /root/reference is present
+    the reference AudioAutoencoder is driven with the same fakes and must agree bit-for-bit."""
+    from oracle import ref_shims
+    from stable_audio_tools.models.autoencoders import AudioAutoencoder
+    ae = AudioAutoencoder(_FakeEnc(), _FakeDec(), latent_dim=3, downsampling_ratio=4, sample_rate=16000, io_channels=2,
+                          bottleneck=None)
+    torch.manual_seed(0)
+    a = torch.randn(2, 2, 4 * 37)
+    z = torch.randn(2, 3, 41)
+    enc_c = ae.encode_audio(a.clone(), chunked=True, chunk_size=8, overlap=2, max_batch_size=3)
+    dec_c = ae.decode_audio(z.clone(), chunked=True, chunk_size=8, overlap=2, max_batch_size=2)
+    rec_c = ae.reconstruct_audio(a.clone(), chunked=True, chunk_size=8, overlap=2, max_batch_size=4)
+    assert enc_c.shape == (2, 3, 37) and dec_c.shape == (2, 2, 41 * 4) and rec_c.shape == a.shape
+    assert rel_l2(enc_c, ae.encode_audio(a, chunked=False)) < 1e-5
+    assert rel_l2(dec_c, ae.decode_audio(z, chunked=False)) < 1e-5
+    if ref_shims.reference_available():
+        ref = ref_shims.import_reference()
+        theirs = ref.autoencoders.AudioAutoencoder(_FakeEnc(), _FakeDec(), latent_dim=3, downsampling_ratio=4,
+                                                   sample_rate=16000, io_channels=2, bottleneck=None)
+        assert torch.equal(enc_c, theirs.encode_audio(a.clone(), chunked=True, chunk_size=8, overlap=2, max_batch_size=3))
+        assert torch.equal(dec_c, theirs.decode_audio(z.clone(), chunked=True, chunk_size=8, overlap=2, max_batch_size=2))
+        assert torch.equal(rec_c, theirs.reconstruct_audio(a.clone(), chunked=True, chunk_size=8, overlap=2, max_batch_size=4))
+
+
+def test_vae_bottleneck_sampling_follows_the_torch_rng():
+    from oracle import oobleck_oracle as oo
+    from stable_audio_tools.models.bottleneck import VAEBottleneck
+    h = torch.randn(2, 8, 5)
+    torch.manual_seed(3)
+    z = VAEBottleneck().encode(h)
+    torch.manual_seed(3)
+    noise = torch.randn(2, 4, 5)
+    assert torch.allclose(z, oo.vae_encode(h, noise))
+
+
+def test_rank_sharding_is_a_partition():
+    from stable_audio_tools.utils.torch_common import shard_for_rank
+    items = list(range(64))
+    for world in (1, 2, 4, 8, 5):
+        shards = [shard_for_rank(items, r, world) for r in range(world)]
+        assert sorted(sum(shards, [])) == items
+        assert shards[0] == items[0::world]
+
+
+def test_gloo_world_size_2_conditioning_broadcast_and_sharding(tmp_path):
+    """The N>1 host path of bench.py / generate: rank 0 owns the conditioning, one broadcast, then
+    items[rank::world] - run with 2 gloo processes on CPU."""
+    script = tmp_path / "w.py"
+    script.write_text(f"""
+import os, sys, torch, torch.distributed as td
+sys.path.insert(0, {os.path.join(ROOT, 'friendly-stable-audio-tools_b200')!r})
+from stable_audio_tools.utils.torch_common import shard_for_rank, get_rank, get_world_size
+td.init_process_group('gloo')
+r, w = get_rank(), get_world_size()
+g = torch.Generator().manual_seed(7)
+cond = torch.randn(8, 5, 3, generator=g) if r == 0 else torch.zeros(8, 5, 3)
+td.broadcast(cond, 0)
+mine = cond[r::w]
+want = torch.randn(8, 5, 3, generator=torch.Generator().manual_seed(7))[r::w]
+assert torch.equal(mine, want)
+assert shard_for_rank(list(range(8))) == list(range(8))[r::w]
+t = torch.tensor([float(r + 1)])
+td.all_reduce(t, op=td.ReduceOp.MAX)
+assert t.item() == w
+td.destroy_process_group()
+print('rank', r, 'ok')
+""")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "rank 0 ok" in p.stdout and "rank 1 ok" in p.stdout
