@@ -8,11 +8,13 @@
 // K-major weight matrix [taps * N, K].  A plain Linear layer is n_taps = 1,
 // batches = 1.  Accumulation is fp32 in TMEM.
 //
-// Structure (one persistent CTA per SM, 256 threads):
-//   warp 0   TMA producer       global -> 128B-swizzled smem ring (mbarrier full/empty)
-//   warp 1   MMA issuer         one thread issues tcgen05.mma 128xBNx16, commits to mbarriers
-//   warp 2   TMEM allocator     2 x BN fp32 columns (double-buffered accumulator)
-//   warps 4-7 epilogue          tcgen05.ld 32 lanes x 32 columns -> registers -> fused op -> global
+// Structure (one persistent CTA per SM, 384 threads):
+//   warp 0    TMA producer      global -> 128B-swizzled smem ring (mbarrier full/empty)
+//   warp 1    MMA issuer        one thread issues tcgen05.mma 128xBNx16, commits to mbarriers
+//   warp 2    TMEM allocator    2 x BN fp32 columns (double-buffered accumulator)
+//   warps 4-11 epilogue         two warps per TMEM lane quadrant (interleaved column chunks):
+//                               tcgen05.ld 32 lanes x 32 columns -> registers -> fused op -> global,
+//                               software-pipelined (the load of chunk c+1 overlaps the math of c)
 // The accumulator is double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include "common.cuh"
@@ -36,7 +38,7 @@ struct GemmShape {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;   // 64 x 16-bit = 128 B = one swizzle atom row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;   // 4 control warps + 8 epilogue warps
 constexpr int kSmemBudget = 220 * 1024;
 
 template <int BN>
@@ -91,7 +93,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 8);
     }
     fence_mbar_init();
   }
@@ -175,7 +177,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int q = warp - 4;  // TMEM lane quadrant == warp % 4
+    const int q = warp & 3;            // TMEM lane quadrant == warp % 4
+    const int half = (warp - 4) >> 2;  // two warps per quadrant take alternate column chunks
+    constexpr int kChunks = BN / Epi::kCols;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -192,18 +196,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       c.row = batch * s.L + c.l;
       c.valid = c.l < s.L;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int cc = 0; cc < BN; cc += Epi::kCols) {
-        if (n0 + cc >= s.N) break;   // warp-uniform
-        uint32_t r[Epi::kCols];
+      int n_valid = (s.N - n0 + Epi::kCols - 1) / Epi::kCols;   // chunks that hold real columns (warp-uniform)
+      if (n_valid > kChunks) n_valid = kChunks;
+      uint32_t r0[Epi::kCols], r1[Epi::kCols];
+      auto load_chunk = [&](int ci, uint32_t (&dst)[Epi::kCols]) {
 #pragma unroll
         for (int j = 0; j < Epi::kCols / 32; ++j) {
-          uint32_t(&rj)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[j * 32]);
-          tmem_ld_32x32(t_row + cc + j * 32, rj);
+          uint32_t(&rj)[32] = *reinterpret_cast<uint32_t(*)[32]>(&dst[j * 32]);
+          tmem_ld_32x32(t_row + ci * Epi::kCols + j * 32, rj);
         }
+      };
+      if (half < n_valid) {
+        load_chunk(half, r0);
         tmem_ld_wait();
-        c.col0 = n0 + cc;
-        Epi::apply(ep, c, r);
+      }
+#pragma unroll 1
+      for (int ci = half; ci < n_valid; ci += 4) {
+        const bool has1 = ci + 2 < n_valid;
+        if (has1) load_chunk(ci + 2, r1);
+        c.col0 = n0 + ci * Epi::kCols;
+        Epi::apply(ep, c, r0);
+        tmem_ld_wait();
+        if (has1) {
+          if (ci + 4 < n_valid) load_chunk(ci + 4, r0);
+          c.col0 = n0 + (ci + 2) * Epi::kCols;
+          Epi::apply(ep, c, r1);
+          tmem_ld_wait();
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -315,9 +334,10 @@ struct EpiResidual {
         const float4 gg = __ldg(g + j);
         v.x *= gg.x; v.y *= gg.y; v.z *= gg.z; v.w *= gg.w;
       }
-      float4 o = dst[j];
-      o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
-      dst[j] = o;
+      // fire-and-forget fp32 vector reduction in L2: every element receives exactly one add
+      // per GEMM (no split-K), so the result is deterministic and no load stalls the epilogue
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                   : "memory");
     }
   }
 };

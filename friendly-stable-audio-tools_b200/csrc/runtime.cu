@@ -5,6 +5,8 @@
 
 #include "common.cuh"
 #include "gemm.cuh"
+#include "kernels.h"
+#include <cstdlib>
 
 namespace satb {
 
@@ -13,6 +15,15 @@ unsigned long long g_launch_count = 0;
 
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 const char* get_last_error() { return g_last_error.c_str(); }
+
+bool attention_use_legacy() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SATB_ATTN");
+    v = (e && std::string(e) == "mma") ? 1 : 0;
+  }
+  return v == 1;
+}
 
 int device_sm_count() {
   static int cached = 0;
