@@ -1,17 +1,19 @@
 // tcgen05 attention forward, head dim 64, no mask, non-causal, optional GQA:
 //   O = softmax(Q K^T / sqrt(64)) V      (reference models/transformer.py:496-536)
 //
-// One CTA = 128 query rows of one (batch item, head); two CTAs are resident per SM so one
-// CTA's softmax overlaps the other's MMAs.  Per 128-key tile:
-//   warp 1 (one thread): S = Q K^T  -> TMEM cols [0,128)        tcgen05.mma, A/B from smem
-//   warps 4-7 (one query row per thread): row max, then P = exp2(S*c - m) -> TMEM cols
-//                        [128,192) as packed 16-bit pairs; row sums in registers (fp32)
-//   warp 1: O += P V -> TMEM cols [192,256)                     tcgen05.mma, A from TMEM,
-//                        B = V tile in smem addressed MN-major (V is [key][d], d contiguous)
-// Q/K/V tiles arrive by TMA (128B swizzle, out-of-range rows zero-filled).  O stays in TMEM
-// for the whole pass: the running max only moves when the new row max exceeds it by more
-// than 2^8 (lazy rescale: exponentials stay <= 256, exact in fp16/bf16 range, sums in fp32),
-// so the O rescale (TMEM load-scale-store) is rare.
+// One CTA = 128 query rows of one (batch item, head); two CTAs are resident per SM.  Keys are
+// processed in tiles of 64 with double-buffered S and P in TMEM, so the tensor pipe runs ahead of
+// the softmax warps:
+//   warp 1 (one thread): S[b] = Q K_j^T -> TMEM (tcgen05.mma, smem operands), issued two tiles
+//                        ahead; O += P[b] V_j (A = P from TMEM, B = V tile addressed MN-major)
+//   warps 4-7 (one query row per thread): one pass over S[b]: P = exp2(S*c - m_ref) -> TMEM as
+//                        packed 16-bit pairs, row sum (fp32) and raw row max in registers
+// TMEM columns: S0 [0,64) S1 [64,128) P0 [128,160) P1 [160,192) O [192,256).
+// Q/K/V tiles arrive by TMA (128B swizzle, out-of-range rows zero-filled); K tiles are released
+// when Q K^T retires, V tiles when P V retires (independent rings).  O stays in TMEM for the whole
+// pass: the reference max m_ref only moves when a tile's row max exceeds it by more than 2^8
+// (lazy rescale: exponentials stay <= 256, sums in fp32), so the O rescale (TMEM load-scale-store)
+// and the recomputation of that tile's P are rare.
 #include "common.cuh"
 #include "gemm.cuh"
 #include "kernels.h"
@@ -22,20 +24,22 @@ namespace satb {
 namespace {
 
 constexpr int kQ = 128;        // query rows per CTA
-constexpr int kK = 128;        // keys per tile
+constexpr int kK = 64;         // keys per tile
 constexpr int kD = 64;         // head dim
-constexpr int kStagesKV = 2;
-constexpr int kTileBytes = kQ * kD * 2;                      // 16 KB
-constexpr int kAttnSmem = kTileBytes * (1 + 2 * kStagesKV) + 1024 + 256;
+constexpr int kStagesK = 4;
+constexpr int kStagesV = 3;
+constexpr int kQBytes = kQ * kD * 2;                         // 16 KB
+constexpr int kKVBytes = kK * kD * 2;                        // 8 KB
+constexpr int kAttnSmem = kQBytes + (kStagesK + kStagesV) * kKVBytes + 1024 + 256;
 constexpr int kTmemColsAttn = 256;
-constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;
+constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;      // S[b] at kColS + 64 b, P[b] at kColP + 32 b
 constexpr float kRescaleThreshold = 8.0f;                    // log2 units
 
 struct AttnTcArgs {
   uint16_t* o;
   int64_t ldo, o_bs;
   int Nq, Nk, group;
-  int q_col, k_col, v_col;   // column offsets (elements) of head 0 inside the q / kv tensor maps
+  int q_col, k_col, v_col;   // column offsets (elements) of head 0 inside the q / k / v tensor maps
   float scale_log2;
 };
 
@@ -51,6 +55,12 @@ __device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t smem_addr) 
   return d;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(256, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -58,15 +68,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
-  uint8_t* sKV = smem + kTileBytes;  // [stage][K | V]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTileBytes * (1 + 2 * kStagesKV));
+  uint8_t* sK = smem + kQBytes;
+  uint8_t* sV = sK + kStagesK * kKVBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStagesV * kKVBytes);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = kv_full + kStagesKV;
-  uint64_t* s_full = kv_empty + kStagesKV;
-  uint64_t* p_ready = s_full + 1;
-  uint64_t* o_full = p_ready + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + kStagesK;
+  uint64_t* v_full = k_empty + kStagesK;
+  uint64_t* v_empty = v_full + kStagesV;
+  uint64_t* s_full = v_empty + kStagesV;   // [2] MMA -> softmax: S[b] holds Q K_j^T
+  uint64_t* p_ready = s_full + 2;          // [2] softmax -> MMA: S[b] consumed, P[b] written
+  uint64_t* pv_done = p_ready + 2;         // [2] MMA -> softmax: P[b] V retired (P[b] free, O updated)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kQ;
@@ -79,13 +92,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < kStagesKV; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+    for (int i = 0; i < kStagesK; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_ready, 128);
-    mbar_init(o_full, 1);
+    for (int i = 0; i < kStagesV; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 128);
+      mbar_init(&pv_done[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -100,16 +119,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------------------------------------------------------- TMA producer
-      mbar_expect_tx(q_full, kTileBytes);
+      mbar_expect_tx(q_full, kQBytes);
       tma_load_4d(sQ, &tmQ, q_full, p.q_col + h * kD, 0, q0, b);
       for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % kStagesKV;
-        const uint32_t ph = (j / kStagesKV) & 1;
-        mbar_wait(&kv_empty[st], ph ^ 1);
-        uint8_t* sk = sKV + st * 2 * kTileBytes;
-        mbar_expect_tx(&kv_full[st], 2 * kTileBytes);
-        tma_load_4d(sk, &tmK, &kv_full[st], p.k_col + hk * kD, 0, j * kK, b);
-        tma_load_4d(sk + kTileBytes, &tmV, &kv_full[st], p.v_col + hk * kD, 0, j * kK, b);
+        const int sk = j % kStagesK, sv = j % kStagesV;
+        mbar_wait(&k_empty[sk], ((j / kStagesK) & 1) ^ 1);
+        mbar_expect_tx(&k_full[sk], kKVBytes);
+        tma_load_4d(sK + sk * kKVBytes, &tmK, &k_full[sk], p.k_col + hk * kD, 0, j * kK, b);
+        mbar_wait(&v_empty[sv], ((j / kStagesV) & 1) ^ 1);
+        mbar_expect_tx(&v_full[sv], kKVBytes);
+        tma_load_4d(sV + sv * kKVBytes, &tmV, &v_full[sv], p.v_col + hk * kD, 0, j * kK, b);
       }
     }
   } else if (warp == 1) {
@@ -117,36 +136,41 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // ------------------------------------------------------------------ MMA issuer
       const uint32_t q_addr = smem_u32(sQ);
       auto issue_qk = [&](int j) {
-        const int st = j % kStagesKV;
-        mbar_wait(&kv_full[st], (j / kStagesKV) & 1);
+        const int st = j % kStagesK, sb = j & 1;
+        mbar_wait(&k_full[st], (j / kStagesK) & 1);
         tc_fence_after();
         const int nk = min(kK, p.Nk - j * kK);
         const int n_mma = (nk + 15) & ~15;
         const uint32_t idesc = make_idesc_f16(kQ, n_mma, BF16);
-        const uint32_t k_addr = smem_u32(sKV + st * 2 * kTileBytes);
+        const uint32_t k_addr = smem_u32(sK + st * kKVBytes);
 #pragma unroll
         for (int ks = 0; ks < kD / 16; ++ks)
-          umma_f16_ss(tmem_base + kColS, make_desc_kmajor_sw128(q_addr + ks * 32),
+          umma_f16_ss(tmem_base + kColS + sb * kK, make_desc_kmajor_sw128(q_addr + ks * 32),
                       make_desc_kmajor_sw128(k_addr + ks * 32), idesc, ks != 0);
-        umma_commit(s_full);
+        umma_commit(&k_empty[st]);   // the K tile is free as soon as these MMAs retire
+        umma_commit(&s_full[sb]);
       };
       mbar_wait(q_full, 0);
       tc_fence_after();
       issue_qk(0);
+      if (n_tiles > 1) issue_qk(1);
       constexpr uint32_t idesc_pv = make_idesc_f16(kQ, kD, BF16, /*b_mn_major=*/true);
       for (int j = 0; j < n_tiles; ++j) {
-        mbar_wait(p_ready, j & 1);   // S_j consumed, P_j written
+        const int sb = j & 1;
+        mbar_wait(&p_ready[sb], (j >> 1) & 1);   // S[sb] consumed, P[sb] written
         tc_fence_after();
-        if (j + 1 < n_tiles) issue_qk(j + 1);
-        const int st = j % kStagesKV;
+        const int st = j % kStagesV;
+        mbar_wait(&v_full[st], (j / kStagesV) & 1);
+        tc_fence_after();
         const int nk = min(kK, p.Nk - j * kK);
         const int ksteps = (nk + 15) >> 4;
-        const uint32_t v_addr = smem_u32(sKV + st * 2 * kTileBytes + kTileBytes);
+        const uint32_t v_addr = smem_u32(sV + st * kKVBytes);
         for (int ks = 0; ks < ksteps; ++ks)
-          umma_f16_ts(tmem_base + kColO, tmem_base + kColP + ks * 8, make_desc_mnmajor_sw128(v_addr + ks * 2048),
-                      idesc_pv, (j | ks) != 0);
-        umma_commit(o_full);
-        umma_commit(&kv_empty[st]);
+          umma_f16_ts(tmem_base + kColO, tmem_base + kColP + sb * (kK / 2) + ks * 8,
+                      make_desc_mnmajor_sw128(v_addr + ks * 2048), idesc_pv, (j | ks) != 0);
+        umma_commit(&pv_done[sb]);
+        umma_commit(&v_empty[st]);
+        if (j + 2 < n_tiles) issue_qk(j + 2);    // S[sb] is free again
       }
     }
   } else if (warp >= 4) {
@@ -154,33 +178,81 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int q = warp - 4;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    float m_used = -INFINITY, l = 0.f;
-    for (int j = 0; j < n_tiles; ++j) {
-      const int nk = min(kK, p.Nk - j * kK);
-      const int chunks = (nk + 31) >> 5;
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      // pass 1: row max of the valid keys
-      float mx = -INFINITY;
-      for (int c = 0; c < chunks; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_lane + kColS + c * 32, r);
-        tmem_ld_wait();
+    float m_ref = -INFINITY, l = 0.f;
+    const float sc = p.scale_log2;
+    // One pass over S[sb]: P = exp2(S*c - m_ref) -> P[sb]; returns the row sum, tracks the raw max.
+    auto pass_p = [&](int sb, int nk, float& mx_raw) -> float {
+      float sum = 0.f;
+      uint32_t r0[32], r1[32];
+      const uint32_t s_addr = t_lane + kColS + sb * kK, p_addr = t_lane + kColP + sb * (kK / 2);
+      auto do_chunk = [&](int c, const uint32_t (&r)[32]) {
+        uint32_t w[16];
+        if ((c + 1) * 32 <= nk) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < nk) mx = fmaxf(mx, __uint_as_float(r[i]));
-      }
-      mx *= p.scale_log2;
+          for (int i = 0; i < 16; ++i) {
+            const float s0 = __uint_as_float(r[2 * i]), s1 = __uint_as_float(r[2 * i + 1]);
+            mx_raw = fmaxf(fmaxf(mx_raw, s0), s1);
+            const float p0 = ex2_approx(fmaf(s0, sc, -m_ref));
+            const float p1 = ex2_approx(fmaf(s1, sc, -m_ref));
+            sum += p0 + p1;
+            w[i] = Op16<BF16>::pack(p0, p1);
+          }
+        } else {
+          const int lim = nk - c * 32;   // valid columns in this (last) chunk
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float s0 = 2 * i < lim ? __uint_as_float(r[2 * i]) : -INFINITY;
+            const float s1 = 2 * i + 1 < lim ? __uint_as_float(r[2 * i + 1]) : -INFINITY;
+            mx_raw = fmaxf(fmaxf(mx_raw, s0), s1);
+            const float p0 = ex2_approx(fmaf(s0, sc, -m_ref));
+            const float p1 = ex2_approx(fmaf(s1, sc, -m_ref));
+            sum += p0 + p1;
+            w[i] = Op16<BF16>::pack(p0, p1);
+          }
+        }
+        tmem_st_32x16(p_addr + c * 16, w);
+      };
+      tmem_ld_32x32(s_addr, r0);
+      if (nk > 32) tmem_ld_32x32(s_addr + 32, r1);
+      tmem_ld_wait();
+      do_chunk(0, r0);
+      if (nk > 32) do_chunk(1, r1);
+      return sum;
+    };
+    for (int j = 0; j < n_tiles; ++j) {
+      const int sb = j & 1;
+      const int nk = min(kK, p.Nk - j * kK);
+      mbar_wait(&s_full[sb], (j >> 1) & 1);
+      tc_fence_after();
       if (j == 0) {
-        m_used = mx;
-      } else {
-        mbar_wait(o_full, (j - 1) & 1);   // P V of the previous tile retired: P and O are free
+        // the first tile fixes the reference max before any exponential is taken
+        float mx = -INFINITY;
+        for (int c = 0; c * 32 < nk; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_lane + kColS + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < nk) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+        m_ref = mx * sc;
+      }
+      if (j >= 2) {
+        mbar_wait(&pv_done[sb], ((j - 2) >> 1) & 1);   // P[sb] V_{j-2} retired: P[sb] is free
         tc_fence_after();
-        const bool need = mx > m_used + kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) {
-          const float f = need ? exp2f(m_used - mx) : 1.0f;
-          if (need) m_used = mx;
-          l *= f;
+      }
+      float mx_raw = -INFINITY;
+      float sum = pass_p(sb, nk, mx_raw);
+      // lazy rescale: only when this tile's max exceeds the reference max by more than 2^8
+      const bool need = mx_raw * sc > m_ref + kRescaleThreshold;
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_new = need ? mx_raw * sc : m_ref;
+        const float f = ex2_approx(m_ref - m_new);   // 1 for rows that keep their reference
+        m_ref = m_new;
+        l *= f;
+        if (j > 0) {
+          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // every earlier P V has retired
+          tc_fence_after();
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t r[32];
@@ -194,31 +266,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               tmem_st_32x16(t_lane + kColO + c * 32 + half * 16, w);
             }
           }
-          tmem_st_wait();
         }
+        float dummy = -INFINITY;
+        sum = pass_p(sb, nk, dummy);   // P again with the new reference max
       }
-      // pass 2: P = exp2(S*c - m), packed 16-bit pairs -> TMEM; row sum in fp32
-      for (int c = 0; c < chunks; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_lane + kColS + c * 32, r);
-        tmem_ld_wait();
-        uint32_t w[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int k0 = c * 32 + 2 * i;
-          const float p0 = k0 < nk ? exp2f(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -m_used)) : 0.f;
-          const float p1 = k0 + 1 < nk ? exp2f(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -m_used)) : 0.f;
-          l += p0 + p1;
-          w[i] = Op16<BF16>::pack(p0, p1);
-        }
-        tmem_st_32x16(t_lane + kColP + c * 16, w);
-      }
+      l += sum;
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_ready);
+      mbar_arrive(&p_ready[sb]);
     }
     // epilogue: O / l -> global (128 B per row)
-    mbar_wait(o_full, (n_tiles - 1) & 1);
+    mbar_wait(&pv_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
     tc_fence_after();
     const float inv = 1.0f / l;
     const bool valid = (q0 + row) < p.Nq;
@@ -247,9 +305,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-int make_tmap_rows(CUtensorMap* m, const void* ptr, int cols, int rows, int batches, int64_t ld, int64_t bs) {
-  // (cols, rows, batches) 16-bit, box (64, 128, 1): reuse the A-operand encoder (phase dim = 1)
-  return make_tmap_a(m, ptr, cols, rows, batches, ld, bs, 1);
+int make_tmap_rows(CUtensorMap* m, const void* ptr, int cols, int rows, int batches, int64_t ld, int64_t bs,
+                   int box_rows) {
+  // (cols, rows, batches) 16-bit, box (64, box_rows, 1): reuse the A-operand encoder (phase dim = 1)
+  return make_tmap_a(m, ptr, cols, rows, batches, ld, bs, 1, box_rows);
 }
 
 }  // namespace
@@ -265,9 +324,9 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
   SATB_REQUIRE(Nk >= 1 && Nq >= 1, "empty attention problem");
   SATB_REQUIRE(ldo % 8 == 0, "attention output stride must be 16B aligned");
   CUtensorMap tq, tk, tv;
-  SATB_PROPAGATE(make_tmap_rows(&tq, q, q_cols, Nq, batch, ldq, q_bs));
-  SATB_PROPAGATE(make_tmap_rows(&tk, k, k_cols, Nk, batch, ldk, k_bs));
-  SATB_PROPAGATE(make_tmap_rows(&tv, v, v_cols, Nk, batch, ldv, v_bs));
+  SATB_PROPAGATE(make_tmap_rows(&tq, q, q_cols, Nq, batch, ldq, q_bs, kQ));
+  SATB_PROPAGATE(make_tmap_rows(&tk, k, k_cols, Nk, batch, ldk, k_bs, kK));
+  SATB_PROPAGATE(make_tmap_rows(&tv, v, v_cols, Nk, batch, ldv, v_bs, kK));
   AttnTcArgs a;
   a.o = static_cast<uint16_t*>(o);
   a.ldo = ldo; a.o_bs = o_bs;

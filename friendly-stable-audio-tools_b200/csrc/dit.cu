@@ -83,6 +83,21 @@ static int linear(TmapCache& tc, const void* A, int64_t lda, int M, int K, const
   return launch_gemm<Epi, BN, BF16>(*ta, *tb, s, ep, stream);
 }
 
+// Picks the N tile (256 or 128) that wastes less of the last wave of the persistent grid; the
+// 128-wide tile streams as many smem bytes per MMA cycle as the tensor pipe can take, so it is
+// only preferred when it clearly wins on wave quantisation.
+template <class Epi, bool BF16>
+static int linear_auto(TmapCache& tc, const void* A, int64_t lda, int M, int K, const void* W, int N,
+                       const typename Epi::Params& ep, cudaStream_t stream) {
+  const double sms = device_sm_count();
+  auto eff = [&](int bn) {
+    const double waves = static_cast<double>(ceil_div(M, kBlockM)) * ceil_div(N, bn) / sms;
+    return waves / std::ceil(waves);
+  };
+  if (N % 128 == 0 && eff(128) * 0.9 > eff(256)) return linear<Epi, 128, BF16>(tc, A, lda, M, K, W, N, ep, stream);
+  return linear<Epi, 256, BF16>(tc, A, lda, M, K, W, N, ep, stream);
+}
+
 struct LayerW {
   float *pre_g = nullptr, *pre_b = nullptr, *ca_g = nullptr, *ca_b = nullptr, *ff_g = nullptr, *ff_b = nullptr;
   uint16_t *w_qkv = nullptr, *w_o = nullptr, *w_q = nullptr, *w_kv = nullptr, *w_co = nullptr, *w_ff1 = nullptr,
@@ -548,7 +563,7 @@ static int dit_forward_impl(SatbDit* d, const float* x, const float* t, float* o
     {
       ProfScope ps(d, PROF_ATTN_OUT, st);
       EpiResidual::Params ep{h, D, nullptr, ssg_l ? ssg_l + 2 * D : nullptr, N_seq, static_cast<int>(ssg_ld), B};
-      SATB_PROPAGATE((linear<EpiResidual, 256, BF16>(d->tmaps, att, D, M, D, W.w_o, D, ep, st)));
+      SATB_PROPAGATE((linear_auto<EpiResidual, BF16>(d->tmaps, att, D, M, D, W.w_o, D, ep, st)));
     }
     // ---- cross-attention on the rows that have a non-null context
     if (Mc > 0) {
@@ -558,7 +573,7 @@ static int dit_forward_impl(SatbDit* d, const float* x, const float* t, float* o
       {
         typedef EpiStore16<BF16> E;
         typename E::Params ep{q16, D, nullptr, 0};
-        SATB_PROPAGATE((linear<E, 256, BF16>(d->tmaps, a16, D, Mc, D, W.w_q, D, ep, st)));
+        SATB_PROPAGATE((linear_auto<E, BF16>(d->tmaps, a16, D, Mc, D, W.w_q, D, ep, st)));
       }
       const uint16_t* kv = d->ws_kv.as<uint16_t>() + static_cast<size_t>(i) * d->Rc * d->Mctx * 2 * d->ce;
       const int64_t kvs = static_cast<int64_t>(d->Mctx) * 2 * d->ce;
@@ -572,7 +587,7 @@ static int dit_forward_impl(SatbDit* d, const float* x, const float* t, float* o
                                            d->ce, d->Rc, H, Hkv, N_seq, d->Mctx, BF16, st));
       {
         EpiResidual::Params ep{h, D, nullptr, nullptr, N_seq, 0, 1};
-        SATB_PROPAGATE((linear<EpiResidual, 256, BF16>(d->tmaps, att, D, Mc, D, W.w_co, D, ep, st)));
+        SATB_PROPAGATE((linear_auto<EpiResidual, BF16>(d->tmaps, att, D, Mc, D, W.w_co, D, ep, st)));
       }
     }
     // ---- feed-forward: LN -> GEMM (+bias, SwiGLU) -> GEMM (+bias, +residual)
@@ -590,7 +605,7 @@ static int dit_forward_impl(SatbDit* d, const float* x, const float* t, float* o
     {
       ProfScope ps(d, PROF_FF_OUT, st);
       EpiResidual::Params ep{h, D, W.b_ff2, ssg_l ? ssg_l + 5 * D : nullptr, N_seq, static_cast<int>(ssg_ld), B};
-      SATB_PROPAGATE((linear<EpiResidual, 256, BF16>(d->tmaps, ff, d->ffi, M, d->ffi, W.w_ff2, D, ep, st)));
+      SATB_PROPAGATE((linear_auto<EpiResidual, BF16>(d->tmaps, ff, d->ffi, M, d->ffi, W.w_ff2, D, ep, st)));
     }
   }
   if (hidden_out)

@@ -532,7 +532,7 @@ struct EpiStoreNCL {
 
 // ------------------------------------------------------------------ host side
 int make_tmap_a(CUtensorMap* m, const void* ptr, int K, int L, int batches, int64_t row_stride_elems,
-                int64_t batch_stride_elems, int stride = 1);
+                int64_t batch_stride_elems, int stride = 1, int box_rows = kBlockM);
 int make_tmap_b(CUtensorMap* m, const void* ptr, int K, int rows, int64_t row_stride_elems, int box_rows);
 
 template <class Epi, int BN, bool BF16>

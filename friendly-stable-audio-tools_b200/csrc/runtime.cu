@@ -57,7 +57,7 @@ static EncodeTiledFn get_encode_fn() {
 // (stride 1 for everything but strided convolutions), box (64, 1, 128, 1), 128B swizzle,
 // zero OOB fill.  L = number of rows (positions / stride).
 int make_tmap_a(CUtensorMap* m, const void* ptr, int K, int L, int batches, int64_t row_stride_elems,
-                int64_t batch_stride_elems, int stride) {
+                int64_t batch_stride_elems, int stride, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   SATB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
   SATB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base must be 16B aligned");
@@ -67,7 +67,7 @@ int make_tmap_a(CUtensorMap* m, const void* ptr, int K, int L, int batches, int6
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(row_stride_elems) * 2,
                            static_cast<cuuint64_t>(row_stride_elems) * 2 * stride,
                            static_cast<cuuint64_t>(batch_stride_elems) * 2};
-  cuuint32_t box[4] = {static_cast<cuuint32_t>(kBlockK), 1, static_cast<cuuint32_t>(kBlockM), 1};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(kBlockK), 1, static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -282,9 +282,11 @@ def dit_param_shapes(cfg):
 def make_dit_weights(cfg, seed=0, std=0.02, dtype=torch.float32):
     """Deterministic synthetic weights.  Every tensor the reference zero-inits
     (to_out, ff.2, pre/postprocess_conv, to_scale_shift_gate) is
-    re-randomised so parity is not vacuous; to_qkv / to_q / to_kv get a larger
-    std so the softmax is not near-uniform.  LN gamma ~ 1 + N(0, 0.1), beta = 0
-    (a buffer in the reference).  inv_freq follows transformer.py:115."""
+    re-randomised so parity is not vacuous; to_qkv / to_q / to_kv are scaled so
+    the attention logits q.k/sqrt(d) have a standard deviation of about 2 for
+    unit-variance inputs at any width (neither near-uniform nor one-hot softmax:
+    std 0.02 would give ~0.6 at D=1536 and ~0.02 at D=256).  LN gamma ~ 1 + N(0, 0.1),
+    beta = 0 (a buffer in the reference).  inv_freq follows transformer.py:115."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
     for k, shp in dit_param_shapes(cfg).items():
@@ -300,7 +302,8 @@ def make_dit_weights(cfg, seed=0, std=0.02, dtype=torch.float32):
         elif k.endswith("bias"):
             sd[k] = torch.randn(shp, generator=g) * std
         elif "to_qkv" in k or "to_q." in k or "to_kv" in k:
-            sd[k] = torch.randn(shp, generator=g) * (3.0 * std)
+            # logits = q.k/8 with q, k ~ N(0, fan_in * s^2) per element: std = fan_in * s^2
+            sd[k] = torch.randn(shp, generator=g) * math.sqrt(2.0 / shp[1])
         elif "preprocess_conv" in k or "postprocess_conv" in k:
             sd[k] = torch.randn(shp, generator=g) * (2.0 * std)
         else:

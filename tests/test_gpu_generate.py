@@ -1,0 +1,99 @@
+"""GPU end-to-end: generate_diffusion_cond (drop-in orchestration -> restated dpmpp sampler -> native
+DiT -> native Oobleck decode) against the same pipeline driven by the CPU oracle, with the initial
+noise and the per-step SDE noise injected into both loops.
+
+Tolerance: errors of the fp16-operand denoiser compound through the sampler steps; gate rel-L2 <= 3e-2
+on the final latents after 6 steps with CFG 5, and <= 5e-2 on the decoded audio."""
+import pytest
+import torch
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+DIT = dict(io_channels=8, embed_dim=256, depth=2, num_heads=4, cond_token_dim=128, global_cond_dim=256,
+           project_cond_tokens=False, transformer_type="continuous_transformer")
+DEC = dict(out_channels=2, channels=32, c_mults=[1, 2, 4], strides=[2, 4, 8], latent_dim=8, use_snake=True, final_tanh=False)
+ENC = dict(in_channels=2, channels=32, c_mults=[1, 2, 4], strides=[2, 4, 8], latent_dim=16, use_snake=True)
+
+
+class _StubConditioner(torch.nn.Module):
+    def set_device(self, device):
+        pass
+
+
+def _build():
+    from oracle import dit_oracle as do
+    from oracle import oobleck_oracle as oo
+    from stable_audio_tools.models.autoencoders import AudioAutoencoder, OobleckDecoder, OobleckEncoder
+    from stable_audio_tools.models.bottleneck import VAEBottleneck
+    from stable_audio_tools.models.diffusion import ConditionedDiffusionModelWrapper, DiTWrapper
+    from stable_audio_tools.models.pretransforms import AutoencoderPretransform
+    # io_channels must be a multiple of 32 for the native path: 64 latent channels, decoder latent_dim 64
+    cfg = dict(DIT, io_channels=64)
+    dit_sd = do.make_dit_weights(cfg, seed=1)
+    dec_cfg = dict(DEC, latent_dim=64)
+    wrapper = DiTWrapper(**cfg)
+    wrapper.model.load_state_dict(dit_sd)
+    dsd = oo.make_oobleck_weights(oo.decoder_param_shapes(dec_cfg), seed=2, transposed=oo.decoder_transposed_prefixes(dec_cfg))
+    esd = oo.make_oobleck_weights(oo.encoder_param_shapes(dict(ENC, latent_dim=128)), seed=3)
+    dec, enc = OobleckDecoder(**dec_cfg), OobleckEncoder(**dict(ENC, latent_dim=128))
+    dec.load_state_dict(dsd)
+    enc.load_state_dict(esd)
+    ae = AudioAutoencoder(enc, dec, latent_dim=64, downsampling_ratio=64, sample_rate=16000, io_channels=2,
+                          bottleneck=VAEBottleneck())
+    pre = AutoencoderPretransform(ae, scale=1.0, iterate_batch=True)
+    model = ConditionedDiffusionModelWrapper(wrapper, _StubConditioner(), io_channels=64, sample_rate=16000,
+                                             min_input_length=64, pretransform=pre,
+                                             cross_attn_cond_ids=["prompt", "seconds_start", "seconds_total"],
+                                             global_cond_ids=["seconds_start", "seconds_total"]).cuda().eval()
+    return model, cfg, dit_sd, dec_cfg, dsd
+
+
+@pytest.mark.parametrize("sampler", ["dpmpp-3m-sde", "dpmpp-2m-sde"])
+def test_generate_matches_oracle_pipeline(sampler):
+    from oracle import dit_oracle as do
+    from oracle import oobleck_oracle as oo
+    from oracle import sampler_oracle as so
+    from stable_audio_tools.inference.generation import generate_diffusion_cond
+    model, cfg, dit_sd, dec_cfg, dsd = _build()
+    B, L, steps, seed, cfg_scale = 2, 48, 6, 321, 5.0
+    g = torch.Generator().manual_seed(5)
+    cond = {"prompt": (torch.randn(B, 10, 128, generator=g).cuda(), torch.ones(B, 10).cuda()),
+            "seconds_start": (torch.randn(B, 1, 128, generator=g).cuda(), torch.ones(B, 1).cuda()),
+            "seconds_total": (torch.randn(B, 1, 128, generator=g).cuda(), torch.ones(B, 1).cuda())}
+    sde_noise = [torch.randn(B, 64, L, generator=g) for _ in range(steps)]
+
+    def make_ns(dev):
+        it = iter(sde_noise)
+        return lambda s, sn: next(it).to(dev)
+
+    lat = generate_diffusion_cond(model, steps=steps, cfg_scale=cfg_scale, conditioning_tensors=cond,
+                                  sample_size=L * 64, seed=seed, device="cuda", return_latents=True,
+                                  sampler_type=sampler, sigma_min=0.3, sigma_max=50.0, noise_sampler=make_ns("cuda"))
+    audio = model.pretransform.decode(lat)
+    # oracle pipeline with the same initial noise (drawn from the CUDA generator exactly as the orchestrator does)
+    torch.manual_seed(seed)
+    noise = torch.randn([B, 64, L], device="cuda").cpu()
+    cross = torch.cat([cond[k][0] for k in ("prompt", "seconds_start", "seconds_total")], dim=1).cpu()
+    glob = torch.cat([cond[k][0] for k in ("seconds_start", "seconds_total")], dim=-1).squeeze(1).cpu()
+    # _build() loads the state dict AFTER DiTWrapper's construction-time halving, so the native model
+    # holds dit_sd itself and the oracle uses the same tensors
+    def oracle_fn(x, t, **kw):
+        return do.dit_forward(dit_sd, cfg, x, t, cross_attn_cond=cross, global_embed=glob, cfg_scale=cfg_scale)
+    sigmas = so.get_sigmas_polyexponential(steps, 0.3, 50.0, 1.0)
+    fn = so.sample_dpmpp_3m_sde if "3m" in sampler else so.sample_dpmpp_2m_sde
+    ref_lat = fn(so.VDenoiser(oracle_fn), noise * sigmas[0], sigmas, noise_sampler=make_ns("cpu"))
+    ref_audio = oo.oobleck_decoder(ref_lat, dsd, dec_cfg)
+    assert lat.shape == (B, 64, L) and audio.shape == (B, 2, L * 64)
+    assert rel_l2(lat.cpu(), ref_lat) < 3e-2
+    assert rel_l2(audio.cpu(), ref_audio) < 5e-2
+
+
+def test_ditwrapper_halves_parameters_like_the_reference():
+    from stable_audio_tools.models.diffusion import DiTWrapper
+    torch.manual_seed(0)
+    w = DiTWrapper(**dict(DIT, io_channels=64))
+    g = w.model.transformer.layers[0].pre_norm.gamma
+    assert torch.allclose(g, torch.full_like(g, 0.5))          # ones * 0.5 (diffusion.py:487-489)
+    assert float(w.model.transformer.rotary_pos_emb.inv_freq[0]) == 1.0   # buffers are not halved
