@@ -53,4 +53,13 @@ int satb_attention(const void* q16, const void* k16, const void* v16, void* o16,
                              static_cast<cudaStream_t>(stream));
 }
 
+// Debug: same as satb_attention, plus a clock64 trace of one CTA into dbg[tiles * 12] (device memory).
+int satb_attention_trace(const void* q16, const void* k16, const void* v16, void* o16, int B, int H, int Hkv, int Nq,
+                         int Nk, int bf16, unsigned long long* dbg, void* stream) {
+  const int64_t dq = static_cast<int64_t>(H) * 64, dk = static_cast<int64_t>(Hkv) * 64;
+  return launch_attention_tc(q16, k16, v16, o16, dq, dk, dk, dq, Nq * dq, Nk * dk, Nk * dk, Nq * dq, static_cast<int>(dq),
+                             static_cast<int>(dk), static_cast<int>(dk), 0, 0, 0, B, H, Hkv, Nq, Nk, bf16 != 0,
+                             static_cast<cudaStream_t>(stream), dbg);
+}
+
 }  // extern "C"

@@ -4,8 +4,10 @@
 // One CTA = 128 query rows of one (batch item, head); two CTAs are resident per SM.  Keys are
 // processed in tiles of 64 with double-buffered S and P in TMEM, so the tensor pipe runs ahead of
 // the softmax warps:
-//   warp 1 (one thread): S[b] = Q K_j^T -> TMEM (tcgen05.mma, smem operands), issued two tiles
-//                        ahead; O += P[b] V_j (A = P from TMEM, B = V tile addressed MN-major)
+//   warp 1 (one thread): S[b] = Q K_j^T -> TMEM (tcgen05.mma, smem operands), two tiles ahead
+//   warp 3 (one thread): O += P[b] V_j (A = P from TMEM, B = V tile addressed MN-major); the two
+//                        products are issued by different threads because a tcgen05.mma issue
+//                        costs ~100 cycles of the issuing thread (measured, profiles/)
 //   warps 4-7 (one query row per thread): one pass over S[b]: P = exp2(S*c - m_ref) -> TMEM as
 //                        packed 16-bit pairs, row sum (fp32) and raw row max in registers
 // TMEM columns: S0 [0,64) S1 [64,128) P0 [128,160) P1 [160,192) O [192,256).
@@ -30,7 +32,7 @@ constexpr int kStagesK = 4;
 constexpr int kStagesV = 3;
 constexpr int kQBytes = kQ * kD * 2;                         // 16 KB
 constexpr int kKVBytes = kK * kD * 2;                        // 8 KB
-constexpr int kAttnSmem = kQBytes + (kStagesK + kStagesV) * kKVBytes + 1024 + 256;
+constexpr int kAttnSmem = kQBytes + (kStagesK + kStagesV) * kKVBytes + 1024 + 256 + 2048;   // + row exchange [2][2][128] fp32
 constexpr int kTmemColsAttn = 256;
 constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;      // S[b] at kColS + 64 b, P[b] at kColP + 32 b
 constexpr float kRescaleThreshold = 8.0f;                    // log2 units
@@ -41,6 +43,7 @@ struct AttnTcArgs {
   int Nq, Nk, group;
   int q_col, k_col, v_col;   // column offsets (elements) of head 0 inside the q / k / v tensor maps
   float scale_log2;
+  unsigned long long* dbg;   // optional per-phase clock64 trace of one CTA (profiles/, tests only)
 };
 
 // V tile as the MN-major B operand: rows = keys (K dim), 64 contiguous 16-bit d values (128 B,
@@ -133,10 +136,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ------------------------------------------------------------------ MMA issuer
+      // ------------------------------------------------- MMA issuer 1: S[b] = Q K_j^T, two tiles ahead
       const uint32_t q_addr = smem_u32(sQ);
-      auto issue_qk = [&](int j) {
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      for (int j = 0; j < n_tiles; ++j) {
         const int st = j % kStagesK, sb = j & 1;
+        if (j >= 2) {
+          mbar_wait(&p_ready[sb], ((j - 2) >> 1) & 1);   // S[sb] of tile j-2 has been consumed
+          tc_fence_after();
+        }
         mbar_wait(&k_full[st], (j / kStagesK) & 1);
         tc_fence_after();
         const int nk = min(kK, p.Nk - j * kK);
@@ -149,19 +158,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                       make_desc_kmajor_sw128(k_addr + ks * 32), idesc, ks != 0);
         umma_commit(&k_empty[st]);   // the K tile is free as soon as these MMAs retire
         umma_commit(&s_full[sb]);
-      };
-      mbar_wait(q_full, 0);
-      tc_fence_after();
-      issue_qk(0);
-      if (n_tiles > 1) issue_qk(1);
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      // ------------------------------------------------- MMA issuer 2: O += P[b] V_j
       constexpr uint32_t idesc_pv = make_idesc_f16(kQ, kD, BF16, /*b_mn_major=*/true);
+      const bool trace = p.dbg != nullptr && blockIdx.x == 3 && blockIdx.y == 11 && blockIdx.z == (gridDim.z - 1);
       for (int j = 0; j < n_tiles; ++j) {
         const int sb = j & 1;
-        mbar_wait(&p_ready[sb], (j >> 1) & 1);   // S[sb] consumed, P[sb] written
+        if (trace) p.dbg[j * 12 + 6] = clock64();
+        mbar_wait(&p_ready[sb], (j >> 1) & 1);   // P[sb] written
         tc_fence_after();
+        if (trace) p.dbg[j * 12 + 7] = clock64();
         const int st = j % kStagesV;
         mbar_wait(&v_full[st], (j / kStagesV) & 1);
         tc_fence_after();
+        if (trace) p.dbg[j * 12 + 8] = clock64();
         const int nk = min(kK, p.Nk - j * kK);
         const int ksteps = (nk + 15) >> 4;
         const uint32_t v_addr = smem_u32(sV + st * kKVBytes);
@@ -170,7 +183,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                       make_desc_mnmajor_sw128(v_addr + ks * 2048), idesc_pv, (j | ks) != 0);
         umma_commit(&pv_done[sb]);
         umma_commit(&v_empty[st]);
-        if (j + 2 < n_tiles) issue_qk(j + 2);    // S[sb] is free again
+        if (trace) p.dbg[j * 12 + 9] = clock64();
       }
     }
   } else if (warp >= 4) {
@@ -219,11 +232,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (nk > 32) do_chunk(1, r1);
       return sum;
     };
+    const bool trace = p.dbg != nullptr && blockIdx.x == 3 && blockIdx.y == 11 && blockIdx.z == (gridDim.z - 1) &&
+                       warp == 4 && lane == 0;
+#define SATB_TRACE(idx) do { if (trace) p.dbg[j * 12 + (idx)] = clock64(); } while (0)
+    // a warp whose 32 rows are all beyond Nq (ragged last query tile: 1025 = 8*128 + 1) only keeps
+    // the barrier protocol going; its P rows are never read back through O
+    const bool warp_active = (q0 + q * 32) < p.Nq;
     for (int j = 0; j < n_tiles; ++j) {
       const int sb = j & 1;
       const int nk = min(kK, p.Nk - j * kK);
+      SATB_TRACE(0);
       mbar_wait(&s_full[sb], (j >> 1) & 1);
       tc_fence_after();
+      SATB_TRACE(1);
+      if (!warp_active) {
+        if (j >= 2) mbar_wait(&pv_done[sb], ((j - 2) >> 1) & 1);
+        tc_fence_before();
+        mbar_arrive(&p_ready[sb]);
+        continue;
+      }
       if (j == 0) {
         // the first tile fixes the reference max before any exponential is taken
         float mx = -INFINITY;
@@ -241,8 +268,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         mbar_wait(&pv_done[sb], ((j - 2) >> 1) & 1);   // P[sb] V_{j-2} retired: P[sb] is free
         tc_fence_after();
       }
+      SATB_TRACE(2);
       float mx_raw = -INFINITY;
       float sum = pass_p(sb, nk, mx_raw);
+      SATB_TRACE(3);
       // lazy rescale: only when this tile's max exceeds the reference max by more than 2^8
       const bool need = mx_raw * sc > m_ref + kRescaleThreshold;
       if (__any_sync(0xffffffffu, need)) {
@@ -274,7 +303,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_ready[sb]);
+      SATB_TRACE(5);
     }
+#undef SATB_TRACE
     // epilogue: O / l -> global (128 B per row)
     mbar_wait(&pv_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
     tc_fence_after();
@@ -319,7 +350,7 @@ int make_tmap_rows(CUtensorMap* m, const void* ptr, int cols, int rows, int batc
 int launch_attention_tc(const void* q, const void* k, const void* v, void* o, int64_t ldq, int64_t ldk, int64_t ldv,
                         int64_t ldo, int64_t q_bs, int64_t k_bs, int64_t v_bs, int64_t o_bs, int q_cols, int k_cols,
                         int v_cols, int q_col, int k_col, int v_col, int batch, int H, int H_kv, int Nq, int Nk,
-                        bool bf16, cudaStream_t stream) {
+                        bool bf16, cudaStream_t stream, unsigned long long* dbg) {
   SATB_REQUIRE(H % H_kv == 0, "num_heads must be a multiple of kv heads");
   SATB_REQUIRE(Nk >= 1 && Nq >= 1, "empty attention problem");
   SATB_REQUIRE(ldo % 8 == 0, "attention output stride must be 16B aligned");
@@ -333,6 +364,7 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
   a.Nq = Nq; a.Nk = Nk; a.group = H / H_kv;
   a.q_col = q_col; a.k_col = k_col; a.v_col = v_col;
   a.scale_log2 = (1.0f / sqrtf(64.0f)) * 1.4426950408889634f;
+  a.dbg = dbg;
   dim3 grid(ceil_div(Nq, kQ), H, batch);
   if (bf16) {
     static bool set = false;

@@ -446,8 +446,8 @@ int satb_dit_prepare_cond(SatbDit* d, const float* cross, const float* neg_cross
   SATB_PROPAGATE(d->ws_small.ensure(static_cast<size_t>(2 * B) * (2 * d->F + 4 * D + 6 * D * d->depth) * 4 + 4096));
   SmallWs sw = small_ws(d, 2 * B);
   if (d->has_global) {
-    SATB_PROPAGATE(launch_skinny_linear(global, d->ge0_w, nullptr, nullptr, sw.ge_h, B, d->gd, d->ge, 0, st));
-    SATB_PROPAGATE(launch_skinny_linear(sw.ge_h, d->ge2_w, nullptr, nullptr, sw.ge, B, d->ge, d->ge, 1, st));
+    SATB_PROPAGATE(launch_skinny_linear(global, d->ge0_w, nullptr, nullptr, sw.ge_h, B, d->gd, d->ge, 1, st));
+    SATB_PROPAGATE(launch_skinny_linear(sw.ge_h, d->ge2_w, nullptr, nullptr, sw.ge, B, d->ge, d->ge, 0, st));
   }
   if (d->has_cross) {
     SATB_REQUIRE(Mctx >= 1, "empty cross-attention context");
@@ -521,8 +521,10 @@ static int dit_forward_impl(SatbDit* d, const float* x, const float* t, float* o
 
   // timestep embedding (+ global embedding) -> conditioning token / adaLN vector  (dit.py:176-195)
   SATB_PROPAGATE(launch_fourier(t, d->ts_w, sw.fourier, B, d->F, st));
-  SATB_PROPAGATE(launch_skinny_linear(sw.fourier, d->te0_w, d->te0_b, nullptr, sw.te_h, B, 2 * d->F, D, 0, st));
-  SATB_PROPAGATE(launch_skinny_linear(sw.te_h, d->te2_w, d->te2_b, d->has_global ? sw.ge : nullptr, sw.tok, B, D, D, 1, st));
+  // te_h = silu(W0 f + b0); tok = W2 te_h + b2 (+ global embed); in adaLN mode only silu(tok) is consumed
+  SATB_PROPAGATE(launch_skinny_linear(sw.fourier, d->te0_w, d->te0_b, nullptr, sw.te_h, B, 2 * d->F, D, 1, st));
+  SATB_PROPAGATE(launch_skinny_linear(sw.te_h, d->te2_w, d->te2_b, d->has_global ? sw.ge : nullptr, sw.tok, B, D, D,
+                                      d->adaln ? 1 : 0, st));
   // latent -> token rows, project_in (with the 1x1 pre-conv folded), prepend token
   SATB_PROPAGATE(launch_dit_pre(x, ain, R, B, C, L, P, BF16, st));
   SATB_PROPAGATE((linear<EpiStore32, 256, BF16>(d->tmaps, ain, C, M, C, d->w_in16, D, EpiStore32::Params{h, D, nullptr}, st)));
@@ -531,7 +533,7 @@ static int dit_forward_impl(SatbDit* d, const float* x, const float* t, float* o
     SATB_PROPAGATE(launch_write_prepend(sw.tok, h, R, B, N_seq, D, st));
   } else {
     // adaLN: all layers' scale/shift/gate in one skinny GEMM (transformer.py:648-651,667)
-    SATB_PROPAGATE(launch_skinny_linear(sw.tok, d->w_ssg, nullptr, nullptr, sw.ssg, B, D, d->depth * 6 * D, 1, st));
+    SATB_PROPAGATE(launch_skinny_linear(sw.tok, d->w_ssg, nullptr, nullptr, sw.ssg, B, D, d->depth * 6 * D, 0, st));
     SATB_PROPAGATE(launch_gate_sigmoid(sw.ssg, B, d->depth, D, st));
   }
 

@@ -180,23 +180,24 @@ __device__ __forceinline__ float silu_acc(float x) { return x / (1.0f + expf(-x)
 __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restrict__ in, const float* __restrict__ W,
                                                             const float* __restrict__ bias,
                                                             const float* __restrict__ add, float* __restrict__ out,
-                                                            int R, int K, int N, int silu_in) {
+                                                            int R, int K, int N, int silu_out) {
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
-  const float* wr = W + static_cast<size_t>(n) * K;
+  const float4* wr = reinterpret_cast<const float4*>(W + static_cast<size_t>(n) * K);
+  const int k4n = K >> 2;
   for (int r0 = 0; r0 < R; r0 += 8) {
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-      const float w = __ldg(wr + k);
+#pragma unroll 4
+    for (int k4 = lane; k4 < k4n; k4 += 32) {
+      const float4 w = __ldg(wr + k4);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (r0 + j < R) {
-          float xv = in[static_cast<size_t>(r0 + j) * K + k];
-          if (silu_in) xv = silu_acc(xv);
-          acc[j] = fmaf(xv, w, acc[j]);
+          const float4 x = __ldg(reinterpret_cast<const float4*>(in + static_cast<size_t>(r0 + j) * K) + k4);
+          acc[j] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[j]))));
         }
       }
     }
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restr
       if (lane == 0 && r0 + j < R) {
         float v = s + (bias ? bias[n] : 0.f);
         if (add) v += add[static_cast<size_t>(r0 + j) * N + n];
+        if (silu_out) v = silu_acc(v);
         out[static_cast<size_t>(r0 + j) * N + n] = v;
       }
     }
@@ -345,9 +347,10 @@ int launch_fourier(const float* t, const float* w, float* out, int B, int F, cud
 }
 
 int launch_skinny_linear(const float* in, const float* W, const float* bias, const float* add, float* out, int R,
-                         int K, int N, int silu_in, cudaStream_t stream) {
+                         int K, int N, int silu_out, cudaStream_t stream) {
   SATB_REQUIRE(R >= 1 && R <= 4096, "skinny linear: bad row count");
-  skinny_linear_kernel<<<ceil_div(N, 8), 256, 0, stream>>>(in, W, bias, add, out, R, K, N, silu_in);
+  SATB_REQUIRE(K % 4 == 0, "skinny linear: K must be a multiple of 4");
+  skinny_linear_kernel<<<ceil_div(N, 8), 256, 0, stream>>>(in, W, bias, add, out, R, K, N, silu_out);
   count_launch();
   SATB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -14,7 +14,7 @@ int launch_attention(const void* q, const void* k, const void* v, void* o, int64
 int launch_attention_tc(const void* q, const void* k, const void* v, void* o, int64_t ldq, int64_t ldk, int64_t ldv,
                         int64_t ldo, int64_t q_bs, int64_t k_bs, int64_t v_bs, int64_t o_bs, int q_cols, int k_cols,
                         int v_cols, int q_col, int k_col, int v_col, int batch, int H, int H_kv, int Nq, int Nk,
-                        bool bf16, cudaStream_t stream);
+                        bool bf16, cudaStream_t stream, unsigned long long* dbg = nullptr);
 bool attention_use_legacy();   // SATB_ATTN=mma selects the round-1 mma.sync kernel (debug only)
 
 // ---- elementwise.cu
@@ -29,9 +29,9 @@ int launch_snake_beta(const float* x, const float* alpha, const float* beta, flo
 int launch_dit_pre(const float* x, void* a16, int R, int B_src, int C, int L, int P, bool bf16, cudaStream_t stream);
 // Fourier timestep features [B, 2*F]: cat(cos(2*pi*t*w), sin(2*pi*t*w)).
 int launch_fourier(const float* t, const float* w, float* out, int B, int F, cudaStream_t stream);
-// out[r, n] = sum_k act_in(in[r, k]) * W[n, k] + bias[n] (+ add[r, n]); fp32 weights, R <= 64.
+// out[r, n] = act_out(sum_k in[r, k] * W[n, k] + bias[n] (+ add[r, n])); fp32 weights; act_out = SiLU if silu_out.
 int launch_skinny_linear(const float* in, const float* W, const float* bias, const float* add, float* out, int R,
-                         int K, int N, int silu_in, cudaStream_t stream);
+                         int K, int N, int silu_out, cudaStream_t stream);
 // h[(r*N_seq), :] = tok[r % B, :]  (the prepended global-conditioning token)
 int launch_write_prepend(const float* tok, float* h, int R, int B, int N_seq, int D, cudaStream_t stream);
 // in place: x = sigmoid(1 - x) on column ranges [c0, c0+D) and [c1, c1+D) of every 6D-wide layer block

@@ -107,6 +107,10 @@ int satb_linear_f32out(const void* a16, const void* w16, float* c, int M, int N,
 int satb_attention(const void* q16, const void* k16, const void* v16, void* o16, int B, int H, int Hkv, int Nq, int Nk,
                    int bf16, void* stream);
 
+/* satb_attention plus a clock64 trace (per 64-key tile: 12 slots) of one CTA, for profiles/. */
+int satb_attention_trace(const void* q16, const void* k16, const void* v16, void* o16, int B, int H, int Hkv, int Nq,
+                         int Nk, int bf16, unsigned long long* dbg, void* stream);
+
 /* ---- Oobleck VAE: replaces OobleckDecoder / OobleckEncoder.forward
  *      (models/autoencoders.py:119-194) behind AudioAutoencoder.encode/decode (:268-343) */
 int satb_oobleck_create(const SatbOobleckConfig* cfg, SatbOobleck** out);
