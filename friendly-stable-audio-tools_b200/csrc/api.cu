@@ -30,6 +30,10 @@ int satb_linear_f32out(const void* a16, const void* w16, float* c, int M, int N,
   s.L = M; s.batches = 1; s.N = N; s.K = K; s.n_taps = 1; s.tap_base = 0; s.tap_step = 0; s.b_tap_rows = N; s.stride = 1;
   EpiStore32::Params ep{c, N, nullptr};
   SATB_PROPAGATE(make_tmap_a(&ta, a16, K, M, 1, K, static_cast<int64_t>(M) * K));
+  if ((N % 256 == 0 || N > 256) && gemm_use_2cta() && M >= 1024) {
+    SATB_PROPAGATE(make_tmap_b(&tb, w16, K, N, K, 128));
+    return bf16 ? launch_gemm_2cta<EpiStore32, 256, true>(ta, tb, s, ep, st) : launch_gemm_2cta<EpiStore32, 256, false>(ta, tb, s, ep, st);
+  }
   if (N % 256 == 0 || N > 256) {
     SATB_PROPAGATE(make_tmap_b(&tb, w16, K, N, K, 256));
     return bf16 ? launch_gemm<EpiStore32, 256, true>(ta, tb, s, ep, st) : launch_gemm<EpiStore32, 256, false>(ta, tb, s, ep, st);

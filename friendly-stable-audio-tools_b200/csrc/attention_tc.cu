@@ -118,9 +118,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------------------------------------------------------- TMA producer
       mbar_expect_tx(q_full, kQBytes);
       tma_load_4d(sQ, &tmQ, q_full, p.q_col + h * kD, 0, q0, b);
@@ -135,7 +137,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ------------------------------------------------- MMA issuer 1: S[b] = Q K_j^T, two tiles ahead
       const uint32_t q_addr = smem_u32(sQ);
       mbar_wait(q_full, 0);
@@ -161,7 +163,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
     }
   } else if (warp == 3) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ------------------------------------------------- MMA issuer 2: O += P[b] V_j
       constexpr uint32_t idesc_pv = make_idesc_f16(kQ, kD, BF16, /*b_mn_major=*/true);
       const bool trace = p.dbg != nullptr && blockIdx.x == 3 && blockIdx.y == 11 && blockIdx.z == (gridDim.z - 1);
@@ -369,11 +371,11 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
   if (bf16) {
     static bool set = false;
     if (!set) { SATB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem)); set = true; }
-    attn_tc_kernel<true><<<grid, 256, kAttnSmem, stream>>>(tq, tk, tv, a);
+    SATB_CHECK_CUDA(launch_pdl(attn_tc_kernel<true>, grid, dim3(256), kAttnSmem, stream, tq, tk, tv, a));
   } else {
     static bool set = false;
     if (!set) { SATB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem)); set = true; }
-    attn_tc_kernel<false><<<grid, 256, kAttnSmem, stream>>>(tq, tk, tv, a);
+    SATB_CHECK_CUDA(launch_pdl(attn_tc_kernel<false>, grid, dim3(256), kAttnSmem, stream, tq, tk, tv, a));
   }
   count_launch();
   SATB_CHECK_CUDA(cudaGetLastError());

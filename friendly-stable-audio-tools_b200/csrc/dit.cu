@@ -77,9 +77,16 @@ static int linear(TmapCache& tc, const void* A, int64_t lda, int M, int K, const
                   const typename Epi::Params& ep, cudaStream_t stream) {
   const CUtensorMap *ta, *tb;
   SATB_PROPAGATE(tc.get_a(A, K, M, 1, lda, static_cast<int64_t>(M) * lda, &ta));
-  SATB_PROPAGATE(tc.get_b(W, K, N, K, BN, &tb));
   GemmShape s;
   s.L = M; s.batches = 1; s.N = N; s.K = K; s.n_taps = 1; s.tap_base = 0; s.tap_step = 0; s.b_tap_rows = N; s.stride = 1;
+  if constexpr (BN == 256) {
+    // CTA-pair kernel for the large GEMMs (256 x 256 tiles, half of B per CTA)
+    if (gemm_use_2cta() && M >= 1024) {
+      SATB_PROPAGATE(tc.get_b(W, K, N, K, BN / 2, &tb));
+      return launch_gemm_2cta<Epi, BN, BF16>(*ta, *tb, s, ep, stream);
+    }
+  }
+  SATB_PROPAGATE(tc.get_b(W, K, N, K, BN, &tb));
   return launch_gemm<Epi, BN, BF16>(*ta, *tb, s, ep, stream);
 }
 

@@ -3,6 +3,7 @@
 // All fp32 math; 128-bit global accesses where the layout allows.
 #include "common.cuh"
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace satb {
 
@@ -28,6 +29,8 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
                                                         int rows_per_item, int n_items) {
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= rows) return;
   const int nv = D >> 7;  // float4 per lane
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
@@ -303,14 +306,14 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, void
   SATB_REQUIRE(D % 128 == 0 && D <= kLnMaxVec * 128, "LayerNorm width must be a multiple of 128 and <= 2048");
   if (rows <= 0) return 0;
   const int grid = ceil_div(rows, 4);
+  const int items = n_items > 0 ? n_items : 1;
   if (bf16)
-    layernorm_kernel<true><<<grid, 128, 0, stream>>>(x, gamma, beta, static_cast<uint16_t*>(out16), rows, D, scale,
-                                                     shift, mod_stride, rows_per_item, n_items > 0 ? n_items : 1);
+    SATB_CHECK_CUDA(launch_pdl(layernorm_kernel<true>, dim3(grid), dim3(128), 0, stream, x, gamma, beta,
+                               static_cast<uint16_t*>(out16), rows, D, scale, shift, mod_stride, rows_per_item, items));
   else
-    layernorm_kernel<false><<<grid, 128, 0, stream>>>(x, gamma, beta, static_cast<uint16_t*>(out16), rows, D, scale,
-                                                      shift, mod_stride, rows_per_item, n_items > 0 ? n_items : 1);
+    SATB_CHECK_CUDA(launch_pdl(layernorm_kernel<false>, dim3(grid), dim3(128), 0, stream, x, gamma, beta,
+                               static_cast<uint16_t*>(out16), rows, D, scale, shift, mod_stride, rows_per_item, items));
   count_launch();
-  SATB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -105,9 +105,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // the next kernel may be scheduled as SMs drain
+  pdl_wait();                // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ------------------------------------------------------------ TMA producer
       int stage = 0;
       uint32_t phase = 0;
@@ -140,7 +142,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // -------------------------------------------------------------- MMA issuer
       constexpr uint32_t idesc = make_idesc_f16(kBlockM, BN, BF16);
       int stage = 0;
@@ -238,6 +240,209 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------- CTA-pair variant
+// Same pipeline with two CTAs (one cluster, one TPC) cooperating on a 256 x BN tile through
+// tcgen05.mma.cta_group::2: each CTA loads its own 128 A rows and HALF of the B tile, so the
+// shared-memory traffic per MMA cycle drops from 96 to 64 B/clk per SM and the ring holds 6 stages.
+// CTA 0 issues the MMAs for the pair; the smem-slot and accumulator barriers are signalled in
+// both CTAs by multicast commits; CTA 1's epilogue warps release the accumulator on CTA 0's barrier.
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int kStageA = kBlockM * kBlockK * 2;
+  static constexpr int kStageB = (BN / 2) * kBlockK * 2;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = (kSmemBudget - 1024) / kStage > 8 ? 8 : (kSmemBudget - 1024) / kStage;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStage + 1024 + 256;
+  static_assert(BN == 256 || BN == 128, "BN must be 128/256");
+};
+
+template <class Epi, int BN, bool BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmShape s, const typename Epi::Params ep) {
+  using Cfg = Gemm2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStage);
+  uint64_t* full_bar = bars;                     // used in CTA 0 only (credited by both CTAs' TMA)
+  uint64_t* empty_bar = bars + Cfg::kStages;     // per CTA, multicast-committed
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages; // per CTA, multicast-committed
+  uint64_t* tempty_bar = tfull_bar + 2;          // CTA 0's is the one the MMA thread waits on (16 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  const int m_tiles = (s.L + 2 * kBlockM - 1) / (2 * kBlockM);   // 256-row pair tiles
+  const int n_tiles = (s.N + BN - 1) / BN;
+  const int tiles_per_n = m_tiles * s.batches;
+  const int total_tiles = tiles_per_n * n_tiles;
+  const int kb_per_tap = (s.K + kBlockK - 1) / kBlockK;
+  const int num_kb = kb_per_tap * s.n_taps;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 16);
+    }
+    fence_mbar_init();
+  }
+  cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / TMA credit
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ------------------------------------------------------ TMA producer (both CTAs)
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        const int nt = tile / tiles_per_n;
+        const int rem = tile - nt * tiles_per_n;
+        const int batch = rem / m_tiles;
+        const int m0 = (rem - batch * m_tiles) * 2 * kBlockM + rank * kBlockM;
+        const int n0 = nt * BN + rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / kb_per_tap;
+          const int k0 = (kb - tap * kb_per_tap) * kBlockK;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStage;
+          uint8_t* sb = sa + Cfg::kStageA;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStage);
+          const int u = s.tap_base + tap * s.tap_step;
+          int ph = 0, ro = u;
+          if (s.stride > 1) {
+            ro = (u >= 0) ? u / s.stride : -((-u + s.stride - 1) / s.stride);
+            ph = u - ro * s.stride;
+          }
+          tma_load_4d_2sm(sa, &tmA, &full_bar[stage], k0, ph, m0 + ro, batch);
+          tma_load_2d_2sm(sb, &tmB, &full_bar[stage], k0, tap * s.b_tap_rows + n0);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      // ------------------------------------------------------ MMA issuer (CTA 0 for the pair)
+      constexpr uint32_t idesc = make_idesc_f16(2 * kBlockM, BN, BF16);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStage);
+          const uint32_t b_addr = a_addr + Cfg::kStageA;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = make_desc_kmajor_sw128(a_addr + k * kUmmaK * 2);
+            const uint64_t db = make_desc_kmajor_sw128(b_addr + k * kUmmaK * 2);
+            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tfull_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (both CTAs)
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int kChunks = BN / Epi::kCols;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+      const int nt = tile / tiles_per_n;
+      const int rem = tile - nt * tiles_per_n;
+      const int batch = rem / m_tiles;
+      const int m0 = (rem - batch * m_tiles) * 2 * kBlockM + rank * kBlockM;
+      const int n0 = nt * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      EpiCtx c;
+      c.l = m0 + q * 32 + lane;
+      c.batch = batch;
+      c.row = batch * s.L + c.l;
+      c.valid = c.l < s.L;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      int n_valid = (s.N - n0 + Epi::kCols - 1) / Epi::kCols;
+      if (n_valid > kChunks) n_valid = kChunks;
+      uint32_t r0[Epi::kCols], r1[Epi::kCols];
+      auto load_chunk = [&](int ci, uint32_t (&dst)[Epi::kCols]) {
+#pragma unroll
+        for (int j = 0; j < Epi::kCols / 32; ++j) {
+          uint32_t(&rj)[32] = *reinterpret_cast<uint32_t(*)[32]>(&dst[j * 32]);
+          tmem_ld_32x32(t_row + ci * Epi::kCols + j * 32, rj);
+        }
+      };
+      if (half < n_valid) {
+        load_chunk(half, r0);
+        tmem_ld_wait();
+      }
+#pragma unroll 1
+      for (int ci = half; ci < n_valid; ci += 4) {
+        const bool has1 = ci + 2 < n_valid;
+        if (has1) load_chunk(ci + 2, r1);
+        c.col0 = n0 + ci * Epi::kCols;
+        Epi::apply(ep, c, r0);
+        tmem_ld_wait();
+        if (has1) {
+          if (ci + 4 < n_valid) load_chunk(ci + 4, r0);
+          c.col0 = n0 + (ci + 2) * Epi::kCols;
+          Epi::apply(ep, c, r1);
+          tmem_ld_wait();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);   // the pair's accumulator lock lives in CTA 0
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();   // no CTA may free TMEM / exit while its peer can still signal it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -550,9 +755,28 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape&
   if (total <= 0) return 0;
   int grid = device_sm_count();
   if (grid > total) grid = total;
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, s, ep);
+  SATB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tmA, tmB, s, ep));
   count_launch();
-  SATB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <class Epi, int BN, bool BF16>
+int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const typename Epi::Params& ep,
+                     cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  auto kern = gemm_tcgen05_2cta_kernel<Epi, BN, BF16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int m_tiles = ceil_div(s.L, 2 * kBlockM), n_tiles = ceil_div(s.N, BN);
+  const int total = m_tiles * s.batches * n_tiles;
+  if (total <= 0) return 0;
+  int clusters = device_sm_count() / 2;
+  if (clusters > total) clusters = total;
+  SATB_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tmA, tmB, s, ep));
+  count_launch();
   return 0;
 }
 

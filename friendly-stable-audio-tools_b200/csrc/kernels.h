@@ -15,7 +15,8 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
                         int64_t ldo, int64_t q_bs, int64_t k_bs, int64_t v_bs, int64_t o_bs, int q_cols, int k_cols,
                         int v_cols, int q_col, int k_col, int v_col, int batch, int H, int H_kv, int Nq, int Nk,
                         bool bf16, cudaStream_t stream, unsigned long long* dbg = nullptr);
-bool attention_use_legacy();   // SATB_ATTN=mma selects the round-1 mma.sync kernel (debug only)
+bool attention_use_legacy();
+bool gemm_use_2cta();          // SATB_GEMM=1cta disables the CTA-pair GEMM (A/B debugging)   // SATB_ATTN=mma selects the round-1 mma.sync kernel (debug only)
 
 // ---- elementwise.cu
 // LayerNorm over the last dim (eps 1e-5), optional adaLN modulation y*(1+scale)+shift, 16-bit output.

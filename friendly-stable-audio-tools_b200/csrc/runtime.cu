@@ -25,6 +25,15 @@ bool attention_use_legacy() {
   return v == 1;
 }
 
+bool gemm_use_2cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SATB_GEMM");
+    v = (e && std::string(e) == "1cta") ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int device_sm_count() {
   static int cached = 0;
   if (cached == 0) {
