@@ -392,6 +392,19 @@ def run_native(args):
         tmax = torch.tensor([decode_ms], device=device)
         td.all_reduce(tmax, op=td.ReduceOp.MAX)
         decode_ms = float(tmax.item())
+    # Oobleck decoder roofline bookkeeping, per sample of L = 1024 latents:
+    #   FLOPs 5.163e12; bytes for the fusion level implemented (16-bit activated copy in/out of every
+    #   tensor-core conv, fp32 raw skip stream read+written once per ResidualUnit):
+    dec_flops = 5.163e12
+    dec_bytes = 0.0
+    l_out, chans, strides = LATENT_LEN, [2048, 1024, 512, 256, 128, 128], [8, 8, 4, 4, 2]
+    for i, st_ in enumerate(strides):
+        l_in, l_out = l_out, l_out * st_
+        elems = l_out * chans[i + 1]
+        dec_bytes += 2.0 * l_in * chans[i] + 6.0 * elems        # ConvT: read s16, write raw fp32 + s16
+        dec_bytes += 3 * 4.0 * elems + (12 + 12 + 8) * elems      # 3 x (conv7: 2+2 B) + conv1: 2+4+4+2 (last: no raw write)
+    dec_bytes += 2.0 * l_out * 128 + 4.0 * l_out * 2             # final conv
+    dec_ms_sample = decode_ms / BATCH
     gen_ms = GEN_STEPS * ms_per_step + decode_ms
     audio_sec_per_s = world * BATCH * AUDIO_SECONDS / (gen_ms / 1e3)
 
@@ -434,6 +447,12 @@ def run_native(args):
         "profiled_pass_ms_per_step": profiled_ms_per_step,
         "kernel_breakdown": breakdown,
         "decode_ms_batch": decode_ms, "audio_sec_per_s_100step": audio_sec_per_s,
+        "oobleck_decoder": {"ms_per_sample": dec_ms_sample, "tflops": dec_flops / (dec_ms_sample / 1e3) / 1e12,
+                            "frac_of_tensor_peak": dec_flops / (dec_ms_sample / 1e3) / 1e12 / peak_tf,
+                            "algorithmic_gb_per_sample": dec_bytes / 1e9,
+                            "hbm_gbs": dec_bytes / (dec_ms_sample / 1e3) / 1e9,
+                            "frac_of_hbm_peak": dec_bytes / (dec_ms_sample / 1e3) / 1e9 / (peaks.get("hbm_gbs") or 6650.0),
+                            "note": "5.16 TFLOP per sample sits at the tensor/HBM ridge (SURVEY 0, H2): neither roof is reached"},
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg()

@@ -64,6 +64,30 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): the softmax warps are issue-bound, so the
+// scale-and-shift and the row-sum accumulation process two elements per instruction.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  uint32_t a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+  lo = __uint_as_float(a);
+  hi = __uint_as_float(b);
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(256, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -166,7 +190,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (elect_one()) {
       // ------------------------------------------------- MMA issuer 2: O += P[b] V_j
       constexpr uint32_t idesc_pv = make_idesc_f16(kQ, kD, BF16, /*b_mn_major=*/true);
-      const bool trace = p.dbg != nullptr && blockIdx.x == 3 && blockIdx.y == 11 && blockIdx.z == (gridDim.z - 1);
+      const bool trace = p.dbg != nullptr && blockIdx.x == 3 && blockIdx.y == 11 && blockIdx.z == (gridDim.z / 2);
       for (int j = 0; j < n_tiles; ++j) {
         const int sb = j & 1;
         if (trace) p.dbg[j * 12 + 6] = clock64();
@@ -203,15 +227,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       auto do_chunk = [&](int c, const uint32_t (&r)[32]) {
         uint32_t w[16];
         if ((c + 1) * 32 <= nk) {
+          const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_ref, -m_ref);
+          uint64_t sum2 = pack2(0.f, 0.f);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float s0 = __uint_as_float(r[2 * i]), s1 = __uint_as_float(r[2 * i + 1]);
             mx_raw = fmaxf(fmaxf(mx_raw, s0), s1);
-            const float p0 = ex2_approx(fmaf(s0, sc, -m_ref));
-            const float p1 = ex2_approx(fmaf(s1, sc, -m_ref));
-            sum += p0 + p1;
+            float t0, t1;
+            unpack2(ffma2(pack2(s0, s1), sc2, nm2), t0, t1);
+            const float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+            sum2 = fadd2(sum2, pack2(p0, p1));
             w[i] = Op16<BF16>::pack(p0, p1);
           }
+          float a0, a1;
+          unpack2(sum2, a0, a1);
+          sum += a0 + a1;
         } else {
           const int lim = nk - c * 32;   // valid columns in this (last) chunk
 #pragma unroll
@@ -234,7 +264,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (nk > 32) do_chunk(1, r1);
       return sum;
     };
-    const bool trace = p.dbg != nullptr && blockIdx.x == 3 && blockIdx.y == 11 && blockIdx.z == (gridDim.z - 1) &&
+    const bool trace = p.dbg != nullptr && blockIdx.x == 3 && blockIdx.y == 11 && blockIdx.z == (gridDim.z / 2) &&
                        warp == 4 && lane == 0;
 #define SATB_TRACE(idx) do { if (trace) p.dbg[j * 12 + (idx)] = clock64(); } while (0)
     // a warp whose 32 rows are all beyond Nq (ragged last query tile: 1025 = 8*128 + 1) only keeps

@@ -364,9 +364,15 @@ int run_conv_gemm(SatbOobleck* h, const ConvW& cw, const void* in16, int B, int 
     return 0;
   };
   const CUtensorMap* tb;
-  if (s.N >= 256) {
+  if (s.N >= 256 && s.L >= 512 && gemm_use_2cta()) {
+    SATB_PROPAGATE(get_b(128, &tb));   // CTA pair: each CTA loads half of the 256-wide B tile
+    return launch_gemm_2cta<Epi, 256, BF16>(ta, *tb, s, ep, st);
+  } else if (s.N >= 256) {
     SATB_PROPAGATE(get_b(256, &tb));
     return launch_gemm<Epi, 256, BF16>(ta, *tb, s, ep, st);
+  } else if (s.N == 128 && s.L >= 512 && gemm_use_2cta()) {
+    SATB_PROPAGATE(get_b(64, &tb));    // CTA pair on 256 x 128 tiles: halves the B traffic of the 128-channel layers
+    return launch_gemm_2cta<Epi, 128, BF16>(ta, *tb, s, ep, st);
   } else if (s.N > 64) {
     SATB_PROPAGATE(get_b(128, &tb));
     return launch_gemm<Epi, 128, BF16>(ta, *tb, s, ep, st);

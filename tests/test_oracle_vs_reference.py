@@ -99,3 +99,34 @@ def test_sampler_wiring_vs_reference_sample_k(ref):
         b = mine.sample_k(toy, noise.clone(), steps=8, sampler_type=st, sigma_min=0.3, sigma_max=50, device="cpu",
                           noise_sampler=make_ns())
         assert rel_l2(b, a) < 1e-5
+
+
+def test_number_conditioner_and_multiconditioner_match_reference(ref):
+    """The 'next' row conditioners: same state-dict keys and outputs as the reference's."""
+    import importlib
+    import sys
+    from stable_audio_tools.models import conditioners as mine
+    theirs = importlib.import_module  # placeholder to keep flake quiet
+    ref_cond = None
+    saved = {k: v for k, v in sys.modules.items() if k == "stable_audio_tools" or k.startswith("stable_audio_tools.")}
+    try:
+        for k in saved:
+            del sys.modules[k]
+        sys.modules.update(ref.modules)
+        ref_cond = importlib.import_module("stable_audio_tools.models.conditioners")
+    finally:
+        for k in list(sys.modules):
+            if k == "stable_audio_tools" or k.startswith("stable_audio_tools."):
+                del sys.modules[k]
+        sys.modules.update(saved)
+    torch.manual_seed(0)
+    a = ref_cond.NumberConditioner(64, min_val=0, max_val=512)
+    b = mine.NumberConditioner(64, min_val=0, max_val=512)
+    assert set(a.state_dict()) == set(b.state_dict())
+    b.load_state_dict(a.state_dict())
+    xa, ma = a([0.0, 12.5, 600.0])
+    xb, mb = b([0.0, 12.5, 600.0])
+    assert torch.equal(xa, xb) and torch.equal(ma, mb) and xb.shape == (3, 1, 64)
+    mc = mine.MultiConditioner({"seconds_start": b, "seconds_total": mine.NumberConditioner(64, 0, 512)})
+    out = mc([{"seconds_start": 0, "seconds_total": [30]}, {"seconds_start": 1, "seconds_total": 47}])
+    assert out["seconds_total"][0].shape == (2, 1, 64)
