@@ -41,14 +41,16 @@ constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 384;   // 4 control warps + 8 epilogue warps
 constexpr int kSmemBudget = 220 * 1024;
 
-template <int BN>
+constexpr int kEpiWarps = 8;
+template <int BN, int kEpiStage = 0>   // kEpiStage: bytes of epilogue staging smem per epilogue warp
 struct GemmCfg {
   static constexpr int kStageA = kBlockM * kBlockK * 2;
   static constexpr int kStageB = BN * kBlockK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (kSmemBudget - 1024) / kStage > 8 ? 8 : (kSmemBudget - 1024) / kStage;
+  static constexpr int kAvail = kSmemBudget - 1024 - kEpiWarps * kEpiStage;
+  static constexpr int kStages = kAvail / kStage > 8 ? 8 : kAvail / kStage;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * kEpiStage;
   static_assert(BN == 64 || BN == 128 || BN == 256, "BN must be 64/128/256");
 };
 
@@ -58,13 +60,17 @@ struct EpiCtx {
   int batch;
   int col0;      // first output column of this register chunk
   bool valid;    // row < L
+  int l0;        // first row (within the batch item) of this warp's 32 rows
+  int L;         // rows per batch item
+  int lane;
+  float* stage;  // per-warp staging smem (Epi::kStageBytes), or nullptr
 };
 
 template <class Epi, int BN, bool BF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmShape s, const typename Epi::Params ep) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, Epi::kStageBytes>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStage);
@@ -197,6 +203,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       c.batch = batch;
       c.row = batch * s.L + c.l;
       c.valid = c.l < s.L;
+      c.l0 = m0 + q * 32;
+      c.L = s.L;
+      c.lane = lane;
+      c.stage = Epi::kStageBytes > 0
+                    ? reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStage + 256 + (warp - 4) * Epi::kStageBytes)
+                    : nullptr;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       int n_valid = (s.N - n0 + Epi::kCols - 1) / Epi::kCols;   // chunks that hold real columns (warp-uniform)
       if (n_valid > kChunks) n_valid = kChunks;
@@ -249,14 +261,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // shared-memory traffic per MMA cycle drops from 96 to 64 B/clk per SM and the ring holds 6 stages.
 // CTA 0 issues the MMAs for the pair; the smem-slot and accumulator barriers are signalled in
 // both CTAs by multicast commits; CTA 1's epilogue warps release the accumulator on CTA 0's barrier.
-template <int BN>
+template <int BN, int kEpiStage = 0>
 struct Gemm2Cfg {
   static constexpr int kStageA = kBlockM * kBlockK * 2;
   static constexpr int kStageB = (BN / 2) * kBlockK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (kSmemBudget - 1024) / kStage > 8 ? 8 : (kSmemBudget - 1024) / kStage;
+  static constexpr int kAvail = kSmemBudget - 1024 - kEpiWarps * kEpiStage;
+  static constexpr int kStages = kAvail / kStage > 8 ? 8 : kAvail / kStage;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStage + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStage + 1024 + 256 + kEpiWarps * kEpiStage;
   static_assert(BN == 256 || BN == 128, "BN must be 128/256");
 };
 
@@ -264,7 +277,7 @@ template <class Epi, int BN, bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmShape s, const typename Epi::Params ep) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, Epi::kStageBytes>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStage);
@@ -400,6 +413,12 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       c.batch = batch;
       c.row = batch * s.L + c.l;
       c.valid = c.l < s.L;
+      c.l0 = m0 + q * 32;
+      c.L = s.L;
+      c.lane = lane;
+      c.stage = Epi::kStageBytes > 0
+                    ? reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStage + 256 + (warp - 4) * Epi::kStageBytes)
+                    : nullptr;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       int n_valid = (s.N - n0 + Epi::kCols - 1) / Epi::kCols;
       if (n_valid > kChunks) n_valid = kChunks;
@@ -456,6 +475,7 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)
 template <bool BF16>
 struct EpiStore16 {
   static constexpr int kCols = 32;
+  static constexpr int kStageBytes = 0;
   struct Params {
     void* out;
     int ld;
@@ -487,6 +507,7 @@ struct EpiStore16 {
 // out32[row, col] = acc (+ bias)
 struct EpiStore32 {
   static constexpr int kCols = 32;
+  static constexpr int kStageBytes = 0;
   struct Params {
     float* out;
     int ld;
@@ -512,6 +533,7 @@ struct EpiStore32 {
 //   h[row, col] += (acc + bias[col]) * gate[row / rows_per_item, col]
 struct EpiResidual {
   static constexpr int kCols = 32;
+  static constexpr int kStageBytes = 0;
   struct Params {
     float* h;
     int ld;
@@ -554,6 +576,7 @@ struct EpiResidual {
 template <bool BF16>
 struct EpiQkvRope {
   static constexpr int kCols = 32;
+  static constexpr int kStageBytes = 0;
   struct Params {
     void* out;
     int ld;            // 3*D
@@ -600,6 +623,7 @@ struct EpiQkvRope {
 template <bool BF16>
 struct EpiSwiglu {
   static constexpr int kCols = 64;
+  static constexpr int kStageBytes = 0;
   struct Params {
     void* out;
     int ld;             // inner dim (N/2)
@@ -649,6 +673,7 @@ __device__ __forceinline__ float snake_fast(float v, float a, float ib) {
 template <bool BF16>
 struct EpiConv {
   static constexpr int kCols = 32;
+  static constexpr int kStageBytes = 32 * 36 * 4;   // per-warp [32 rows][32 + 4 pad] fp32 transpose tile
   struct Params {
     const float* bias;    // [cout] or null
     const float* resid;   // fp32 [B*L_out, cout] or null
@@ -661,57 +686,65 @@ struct EpiConv {
     int up;               // transposed-conv stride (1 = ordinary conv)
     int pad;              // transposed-conv padding
   };
+  // Warp-cooperative: the accumulator chunk (thread = row, 32 columns) is transposed through the
+  // per-warp smem tile so that every global access is coalesced (8 lanes x 16 B = one 128 B row
+  // segment, 4 rows per instruction) and each lane needs the per-channel parameters of only 4 channels.
   __device__ static __forceinline__ void apply(const Params& p, const EpiCtx& c, const uint32_t (&r)[32]) {
-    if (!c.valid) return;
+    float* st = c.stage;
     int phase = 0, co0 = c.col0;
     if (p.up > 1) {
       phase = c.col0 / p.cout;
       co0 = c.col0 - phase * p.cout;
     }
-    const int lo = c.l * p.up + phase - p.pad;
-    if (lo < 0 || lo >= p.L_out) return;
-    const size_t base = (static_cast<size_t>(c.batch) * p.L_out + lo) * p.cout + co0;
-    float v[32];
+    const int g = c.lane & 7, r0 = c.lane >> 3;
+    const int co = co0 + 4 * g;
+    // residual (skip) values of this lane's 8 row segments: issued first so that the loads are in
+    // flight during the smem transpose
+    float4 rs[8];
+    size_t idx[8];
+    bool ok[8];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (p.bias) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0) + j);
-        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-      }
+    for (int i = 0; i < 8; ++i) {
+      const int l = c.l0 + r0 + 4 * i;
+      const int lo = l * p.up + phase - p.pad;
+      ok[i] = l < c.L && lo >= 0 && lo < p.L_out;
+      idx[i] = (static_cast<size_t>(c.batch) * p.L_out + (ok[i] ? lo : 0)) * p.cout + co;
+      rs[i] = (ok[i] && p.resid) ? *reinterpret_cast<const float4*>(p.resid + idx[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (p.resid) {
-      const float4* rs = reinterpret_cast<const float4*>(p.resid + base);
+    {
+      float4* mine = reinterpret_cast<float4*>(st + c.lane * 36);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b = rs[j];
-        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-      }
+      for (int j = 0; j < 8; ++j)
+        mine[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                              __uint_as_float(r[4 * j + 3]));
     }
-    if (p.raw_out) {
-      float4* ro = reinterpret_cast<float4*>(p.raw_out + base);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) ro[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), a4 = b4, ib4 = b4;
+    if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+    const bool snake = p.s16_out != nullptr && p.sn_a != nullptr;
+    if (snake) {
+      a4 = __ldg(reinterpret_cast<const float4*>(p.sn_a + co));
+      ib4 = __ldg(reinterpret_cast<const float4*>(p.sn_ib + co));
     }
-    if (p.s16_out) {
-      if (p.sn_a) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(p.sn_a + co0) + j);
-          const float4 ib = __ldg(reinterpret_cast<const float4*>(p.sn_ib + co0) + j);
-          v[4 * j] = snake_fast(v[4 * j], a.x, ib.x);
-          v[4 * j + 1] = snake_fast(v[4 * j + 1], a.y, ib.y);
-          v[4 * j + 2] = snake_fast(v[4 * j + 2], a.z, ib.z);
-          v[4 * j + 3] = snake_fast(v[4 * j + 3], a.w, ib.w);
+    for (int i = 0; i < 8; ++i) {
+      if (ok[i]) {
+        float4 v = *reinterpret_cast<const float4*>(st + (r0 + 4 * i) * 36 + 4 * g);
+        v.x += b4.x + rs[i].x; v.y += b4.y + rs[i].y; v.z += b4.z + rs[i].z; v.w += b4.w + rs[i].w;
+        if (p.raw_out) *reinterpret_cast<float4*>(p.raw_out + idx[i]) = v;
+        if (p.s16_out) {
+          if (snake) {
+            v.x = snake_fast(v.x, a4.x, ib4.x);
+            v.y = snake_fast(v.y, a4.y, ib4.y);
+            v.z = snake_fast(v.z, a4.z, ib4.z);
+            v.w = snake_fast(v.w, a4.w, ib4.w);
+          }
+          *reinterpret_cast<uint2*>(static_cast<uint16_t*>(p.s16_out) + idx[i]) =
+              make_uint2(Op16<BF16>::pack(v.x, v.y), Op16<BF16>::pack(v.z, v.w));
         }
       }
-      uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.s16_out) + base);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        dst[j] = make_uint4(Op16<BF16>::pack(v[8 * j], v[8 * j + 1]), Op16<BF16>::pack(v[8 * j + 2], v[8 * j + 3]),
-                            Op16<BF16>::pack(v[8 * j + 4], v[8 * j + 5]), Op16<BF16>::pack(v[8 * j + 6], v[8 * j + 7]));
     }
+    __syncwarp();
   }
 };
 
@@ -719,18 +752,23 @@ struct EpiConv {
 // per-column store is a coalesced 128 B line.
 struct EpiStoreNCL {
   static constexpr int kCols = 32;
+  static constexpr int kStageBytes = 0;
   struct Params {
     float* out;
     const float* bias;
     int N;
     int L;
+    int do_tanh;
   };
   __device__ static __forceinline__ void apply(const Params& p, const EpiCtx& c, const uint32_t (&r)[32]) {
     if (!c.valid) return;
     float* o = p.out + (static_cast<size_t>(c.batch) * p.N + c.col0) * p.L + c.l;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      if (c.col0 + j < p.N) o[static_cast<size_t>(j) * p.L] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + c.col0 + j) : 0.f);
+      if (c.col0 + j < p.N) {
+        const float v = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + c.col0 + j) : 0.f);
+        o[static_cast<size_t>(j) * p.L] = p.do_tanh ? tanhf(v) : v;
+      }
     }
   }
 };
@@ -743,7 +781,7 @@ int make_tmap_b(CUtensorMap* m, const void* ptr, int K, int rows, int64_t row_st
 template <class Epi, int BN, bool BF16>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const typename Epi::Params& ep,
                 cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, Epi::kStageBytes>;
   auto kern = gemm_tcgen05_kernel<Epi, BN, BF16>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -763,7 +801,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape&
 template <class Epi, int BN, bool BF16>
 int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const typename Epi::Params& ep,
                      cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, Epi::kStageBytes>;
   auto kern = gemm_tcgen05_2cta_kernel<Epi, BN, BF16>;
   static bool attr_set = false;
   if (!attr_set) {

@@ -7,8 +7,9 @@
 // copy of the raw value.  A dilated k=7 convolution is 7 shifted GEMMs accumulated in TMEM
 // (TMA zero-fills the padding); a transposed convolution (k = 2s, stride s) is a 2-tap GEMM
 // over N = s*Cout columns; a strided convolution (k = 2s, stride s) is a 2s-tap GEMM whose
-// taps address the input as (phase, row) through a 4-D tensor map.  The first / last
-// convolutions (2 <-> 128 channels) are bandwidth-bound and stay on CUDA cores.
+// taps address the input as (phase, row) through a 4-D tensor map.  The encoder's first
+// convolution (2 -> 128 channels) is bandwidth-bound and stays on CUDA cores; the decoder's last
+// one (128 -> 2) runs through the same GEMM with a mostly empty N tile.
 // Weight-norm (w = g * v / ||v||, torch.nn.utils.weight_norm via dac.nn.layers) is folded
 // once at load time.
 #include <algorithm>
@@ -146,52 +147,6 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
       typename Op16<BF16>::T h = Op16<BF16>::from_float(snake_fast(acc, a, ib));
       s16[o] = *reinterpret_cast<uint16_t*>(&h);
     }
-  }
-}
-
-// Decoder output convolution (C channels-last 16-bit, already Snake-activated -> Cout = 1 or 2,
-// k taps, no bias, optional tanh), NCL fp32 output.  One thread per output position.
-template <bool BF16>
-__global__ void __launch_bounds__(128) conv_out_kernel(const uint16_t* __restrict__ s16, const float* __restrict__ w,
-                                                       float* __restrict__ audio, int C, int Cout, int64_t T, int kk,
-                                                       int do_tanh) {
-  constexpr int kTile = 128;
-  extern __shared__ uint8_t sm_raw[];
-  // [kTile + kk - 1][C + 2] 16-bit (row stride padded to an odd number of 32-bit words), then weights fp32
-  const int span = kTile + kk - 1, rs = C + 2;
-  uint16_t* sm_x = reinterpret_cast<uint16_t*>(sm_raw);
-  float* sm_w = reinterpret_cast<float*>(sm_raw + ((static_cast<size_t>(span) * rs * 2 + 15) & ~size_t(15)));
-  const int b = blockIdx.y;
-  const int64_t l0 = static_cast<int64_t>(blockIdx.x) * kTile;
-  const int halo = kk / 2;
-  const int cpr = C / 2;  // 32-bit words per row
-  for (int i = threadIdx.x; i < span * cpr; i += blockDim.x) {
-    const int j = i / cpr, cw = i - j * cpr;
-    const int64_t l = l0 + j - halo;
-    uint32_t val = 0;
-    if (l >= 0 && l < T) val = reinterpret_cast<const uint32_t*>(s16 + (static_cast<size_t>(b) * T + l) * C)[cw];
-    reinterpret_cast<uint32_t*>(sm_x + static_cast<size_t>(j) * rs)[cw] = val;
-  }
-  // weights reordered to [co][t][ci]
-  for (int i = threadIdx.x; i < Cout * kk * C; i += blockDim.x) {
-    const int ci = i % C, t = (i / C) % kk, co = i / (C * kk);
-    sm_w[i] = w[(static_cast<size_t>(co) * C + ci) * kk + t];
-  }
-  __syncthreads();
-  const int64_t l = l0 + threadIdx.x;
-  if (l >= T) return;
-  for (int co = 0; co < Cout; ++co) {
-    float acc = 0.f;
-    for (int t = 0; t < kk; ++t) {
-      const uint32_t* xr = reinterpret_cast<const uint32_t*>(sm_x + static_cast<size_t>(threadIdx.x + t) * rs);
-      const float* wr = sm_w + (static_cast<size_t>(co) * kk + t) * C;
-      for (int cw = 0; cw < cpr; ++cw) {
-        const float2 xv = Op16<BF16>::unpack(xr[cw]);
-        acc = fmaf(xv.x, wr[2 * cw], acc);
-        acc = fmaf(xv.y, wr[2 * cw + 1], acc);
-      }
-    }
-    audio[(static_cast<size_t>(b) * Cout + co) * T + l] = do_tanh ? tanhf(acc) : acc;
   }
 }
 
@@ -458,17 +413,13 @@ int decode_impl(SatbOobleck* h, const float* z, float* audio, int B, int L, cuda
     Lc = Lo;
     (void)cin;
   }
-  // final conv k7 chans[0] -> in_channels (audio), no bias, CUDA cores
+  // final conv k7 chans[0] -> audio channels (no bias, optional tanh): the 128 -> 2 contraction runs as a
+  // 7-tap GEMM with the N tile mostly empty (8x wasted MMA work is still ~10x faster than the
+  // shared-memory-bound CUDA-core version it replaces: 1.21 ms -> bandwidth-bound)
   {
     const ConvW& cf = h->convs.at("layers." + std::to_string(n + 2) + ".");
-    const int C = h->chans[0];
-    const size_t smem = ((static_cast<size_t>(128 + cf.k - 1) * (C + 2) * 2 + 15) & ~size_t(15)) +
-                        static_cast<size_t>(cf.cout) * cf.k * C * 4;
-    auto kern = conv_out_kernel<BF16>;
-    SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    dim3 grid(static_cast<unsigned>(ceil_div64(Lc, 128)), B);
-    kern<<<grid, 128, smem, st>>>(static_cast<const uint16_t*>(sA), cf.w32, audio, C, cf.cout, Lc, cf.k, c.final_tanh);
-    count_launch();
+    EpiStoreNCL::Params ep{audio, nullptr, cf.cout, static_cast<int>(Lc), c.final_tanh};
+    SATB_PROPAGATE((run_conv_gemm<EpiStoreNCL, BF16>(h, cf, sA, B, static_cast<int>(Lc), 0, 1, 1, ep, st)));
   }
   SATB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -532,7 +483,7 @@ int encode_impl(SatbOobleck* h, const float* audio, float* latents, int B, int64
   // final conv k3 chans[n] -> latent_dim, NCL fp32 output
   {
     const ConvW& cf = h->convs.at("layers." + std::to_string(n + 2) + ".");
-    EpiStoreNCL::Params ep{latents, cf.bias, cf.cout, static_cast<int>(Lc)};
+    EpiStoreNCL::Params ep{latents, cf.bias, cf.cout, static_cast<int>(Lc), 0};
     SATB_PROPAGATE((run_conv_gemm<EpiStoreNCL, BF16>(h, cf, sA, B, static_cast<int>(Lc), 0, 1, 1, ep, st)));
   }
   return 0;
@@ -615,7 +566,7 @@ int satb_oobleck_finalize(SatbOobleck* h, void* stream) {
       for (int j = 0; j < 3; ++j) SATB_PROPAGATE(res_unit(bp + "layers." + std::to_string(2 + j) + ".", cout));
     }
     SATB_PROPAGATE(prep_snake(h, "layers." + std::to_string(n + 1) + ".", h->chans[0], st));
-    SATB_PROPAGATE(prep_conv(h, "layers." + std::to_string(n + 2) + ".", h->chans[0], c.in_channels, 7, false, true, false, 1, st));
+    SATB_PROPAGATE(prep_conv(h, "layers." + std::to_string(n + 2) + ".", h->chans[0], c.in_channels, 7, false, false, false, 1, st));
     SATB_REQUIRE(h->chans[0] % 2 == 0, "decoder: channels must be even");
   } else {
     SATB_PROPAGATE(prep_conv(h, "layers.0.", c.in_channels, h->chans[0], 7, false, true, true, 1, st));

@@ -90,3 +90,47 @@ def test_dit_full_width_vs_oracle(depth, B, cfg_scale):
     y = m(x.cuda(), t.cuda(), cross_attn_cond=c.cuda(), global_embed=ge.cuda(), cfg_scale=cfg_scale).cpu()
     err = rel_l2(y, ref)
     assert err < tol("fp16", cfg_scale), f"rel l2 {err}"
+
+
+@pytest.mark.parametrize("B,L,M", [(3, 33, 1), (1, 129, 130), (5, 64, 3)])
+def test_dit_ragged_shapes_vs_oracle(B, L, M):
+    """Odd batch sizes, sequence lengths that are not tile multiples, 1-token contexts."""
+    from oracle import dit_oracle as do
+    cfg = dict(io_channels=64, embed_dim=256, depth=2, num_heads=4, cond_token_dim=128, global_cond_dim=256,
+               project_cond_tokens=False, transformer_type="continuous_transformer")
+    sd = do.make_dit_weights(cfg, seed=7)
+    g = torch.Generator().manual_seed(B * 1000 + L)
+    x, t = torch.randn(B, 64, L, generator=g), torch.rand(B, generator=g)
+    c, ge = torch.randn(B, M, 128, generator=g), torch.randn(B, 256, generator=g)
+    m = build_native_dit(cfg, sd)
+    for scale in (1.0, 6.0):
+        ref = do.dit_forward(sd, cfg, x, t, cross_attn_cond=c, global_embed=ge, cfg_scale=scale)
+        y = m(x.cuda(), t.cuda(), cross_attn_cond=c.cuda(), global_embed=ge.cuda(), cfg_scale=scale).cpu()
+        assert rel_l2(y, ref) < tol("fp16", scale)
+
+
+def test_dit_sa2_length_one_block_vs_oracle():
+    """SA-2.0 sequence length (6144 latents + prepend = 6145 tokens, BASELINE configs[4]) at full width,
+    one block, no CFG: 97 key tiles per attention row."""
+    from oracle import dit_oracle as do
+    cfg = dict(SAO_DIT, depth=1)
+    sd = do.make_dit_weights(cfg, seed=8)
+    g = torch.Generator().manual_seed(2)
+    x, t = torch.randn(1, 64, 6144, generator=g), torch.tensor([0.3])
+    c, ge = torch.randn(1, 130, 768, generator=g), torch.randn(1, 1536, generator=g)
+    ref = do.dit_forward(sd, cfg, x, t, cross_attn_cond=c, global_embed=ge, cfg_scale=1.0)
+    y = build_native_dit(cfg, sd)(x.cuda(), t.cuda(), cross_attn_cond=c.cuda(), global_embed=ge.cuda(), cfg_scale=1.0).cpu()
+    assert rel_l2(y, ref) < 2e-3
+
+
+def test_dit_full_width_bf16_vs_oracle():
+    from oracle import dit_oracle as do
+    cfg = dict(SAO_DIT, depth=1)
+    sd = do.make_dit_weights(cfg, seed=9)
+    g = torch.Generator().manual_seed(3)
+    x, t = torch.randn(1, 64, 1024, generator=g), torch.tensor([0.6])
+    c, ge = torch.randn(1, 130, 768, generator=g), torch.randn(1, 1536, generator=g)
+    ref = do.dit_forward(sd, cfg, x, t, cross_attn_cond=c, global_embed=ge, cfg_scale=1.0)
+    y = build_native_dit(cfg, sd, operand_dtype="bf16")(x.cuda(), t.cuda(), cross_attn_cond=c.cuda(),
+                                                        global_embed=ge.cuda(), cfg_scale=1.0).cpu()
+    assert rel_l2(y, ref) < 1.5e-2

@@ -93,3 +93,28 @@ def test_attention_vs_oracle(B, H, Hkv, Nq, Nk):
     heads = lambda t, h: t.float().view(t.shape[0], t.shape[1], h, 64).permute(0, 2, 1, 3)
     ref = attention_core(heads(qh, H), heads(kh, Hkv), heads(vh, Hkv)).permute(0, 2, 1, 3).reshape(B, Nq, H * 64)
     assert rel_l2(o.float().cpu(), ref) < 2e-3
+
+
+def test_attention_lazy_rescale_path_monotone_scores():
+    """Scores that keep growing along the key axis force the reference max to move in (almost)
+    every 64-key tile: exercises the O rescale + P recomputation path of the tcgen05 kernel."""
+    from oracle.dit_oracle import attention_core
+    nat = _native()
+    B, H, Nq, Nk = 1, 2, 200, 700
+    torch.manual_seed(0)
+    q = torch.zeros(B, Nq, H * 64)
+    k = torch.zeros(B, Nk, H * 64)
+    q[..., 0::64] = 4.0                                   # q . k = 4 * k[..., 0]
+    ramp = torch.arange(Nk, dtype=torch.float32) * 0.5    # logits / 8 grow by 0.25 per key (23 log2 units per tile)
+    k[:, :, 0] = ramp
+    k[:, :, 64] = ramp.flip(0)                            # second head: decreasing (max in the first tile)
+    q = q + 0.05 * torch.randn_like(q)
+    v = torch.randn(B, Nk, H * 64)
+    qh, kh, vh = q.half(), k.half(), v.half()
+    o = torch.empty(B, Nq, H * 64, dtype=torch.float16, device="cuda")
+    qd, kd, vd = qh.cuda(), kh.cuda(), vh.cuda()
+    nat.check(nat.lib().satb_attention(nat.ptr(qd), nat.ptr(kd), nat.ptr(vd), nat.ptr(o), B, H, H, Nq, Nk, 0, nat.stream_ptr()))
+    heads = lambda t, h: t.float().view(t.shape[0], t.shape[1], h, 64).permute(0, 2, 1, 3)
+    ref = attention_core(heads(qh, H), heads(kh, H), heads(vh, H)).permute(0, 2, 1, 3).reshape(B, Nq, H * 64)
+    assert torch.isfinite(o).all()
+    assert rel_l2(o.float().cpu(), ref) < 2e-3
