@@ -21,7 +21,7 @@
 
 #include "../../include/satb200.h"
 #include "common.cuh"
-#include "gemm.cuh"
+#include "resunit.cuh"
 #include "kernels.h"
 
 namespace satb {
@@ -275,6 +275,30 @@ int prep_snake(SatbOobleck* h, const std::string& pfx, int c, cudaStream_t st) {
   return 0;
 }
 
+int get_tmap_a(SatbOobleck* h, const void* in16, int cin, int a_rows, int B, int L_in, int a_stride, const CUtensorMap** out) {
+  auto key = std::make_tuple(in16, cin, a_rows, B, static_cast<int64_t>(cin), static_cast<int64_t>(L_in) * cin, a_stride);
+  auto it = h->tmaps.find(key);
+  if (it == h->tmaps.end()) {
+    CUtensorMap m;
+    SATB_PROPAGATE(make_tmap_a(&m, in16, cin, a_rows, B, cin, static_cast<int64_t>(L_in) * cin, a_stride));
+    it = h->tmaps.emplace(key, m).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+int get_tmap_b(SatbOobleck* h, const ConvW& cw, int b_rows, int box, const CUtensorMap** out) {
+  auto key = std::make_tuple(static_cast<const void*>(cw.w16), cw.cin, b_rows, -1, static_cast<int64_t>(cw.cin), int64_t(0), box);
+  auto it = h->tmaps.find(key);
+  if (it == h->tmaps.end()) {
+    CUtensorMap m;
+    SATB_PROPAGATE(make_tmap_b(&m, cw.w16, cw.cin, b_rows, cw.cin, box));
+    it = h->tmaps.emplace(key, m).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
 // One tensor-core convolution.  in16: [B, L_in, cin] 16-bit.  Output positions per item L_out.
 //   kind 0: conv k taps, dilation dil, "same" padding           (L_out = L_in)
 //   kind 1: transposed conv k = 2*up, stride up, pad ceil(up/2)  (L_out = L_in * up)
@@ -298,26 +322,11 @@ int run_conv_gemm(SatbOobleck* h, const ConvW& cw, const void* in16, int B, int 
     s.b_tap_rows = cw.cout; s.stride = factor;
     a_stride = factor; a_rows = L_in / factor;
   }
-  auto key_a = std::make_tuple(in16, cw.cin, a_rows, B, static_cast<int64_t>(cw.cin), static_cast<int64_t>(L_in) * cw.cin, a_stride);
-  auto it = h->tmaps.find(key_a);
-  if (it == h->tmaps.end()) {
-    CUtensorMap m;
-    SATB_PROPAGATE(make_tmap_a(&m, in16, cw.cin, a_rows, B, cw.cin, static_cast<int64_t>(L_in) * cw.cin, a_stride));
-    it = h->tmaps.emplace(key_a, m).first;
-  }
-  const CUtensorMap& ta = it->second;
+  const CUtensorMap* tap;
+  SATB_PROPAGATE(get_tmap_a(h, in16, cw.cin, a_rows, B, L_in, a_stride, &tap));
+  const CUtensorMap& ta = *tap;
   const int b_rows = s.n_taps * s.b_tap_rows;
-  auto get_b = [&](int box, const CUtensorMap** out) -> int {
-    auto key_b = std::make_tuple(static_cast<const void*>(cw.w16), cw.cin, b_rows, -1, static_cast<int64_t>(cw.cin), int64_t(0), box);
-    auto jt = h->tmaps.find(key_b);
-    if (jt == h->tmaps.end()) {
-      CUtensorMap m;
-      SATB_PROPAGATE(make_tmap_b(&m, cw.w16, cw.cin, b_rows, cw.cin, box));
-      jt = h->tmaps.emplace(key_b, m).first;
-    }
-    *out = &jt->second;
-    return 0;
-  };
+  auto get_b = [&](int box, const CUtensorMap** out) -> int { return get_tmap_b(h, cw, b_rows, box, out); };
   const CUtensorMap* tb;
   if (s.N >= 256 && s.L >= 512 && gemm_use_2cta()) {
     SATB_PROPAGATE(get_b(128, &tb));   // CTA pair: each CTA loads half of the 256-wide B tile
@@ -336,18 +345,34 @@ int run_conv_gemm(SatbOobleck* h, const ConvW& cw, const void* in16, int B, int 
   return launch_gemm<Epi, 64, BF16>(ta, *tb, s, ep, st);
 }
 
+// ResidualUnit (models/autoencoders.py:45-68).  In: snake1(x) as 16-bit in sA, x as fp32 in raw.
+// Out: y = x + conv1(snake2(conv7(.))) as fp32 in raw (if keep_raw) and snake_next(y) as 16-bit in sA;
+// sT is scratch (the two pointers are swapped when the fused kernel wrote its output there).
 template <bool BF16>
-int residual_unit(SatbOobleck* h, const std::string& pfx, int C, int B, int L, int dil, float* raw, void* sA, void* sT,
+int residual_unit(SatbOobleck* h, const std::string& pfx, int C, int B, int L, int dil, float* raw, void*& sA, void*& sT,
                   const SnakeW* next_snake, bool keep_raw, cudaStream_t st) {
-  // conv7(dil) on snake1(x) [already in sA] -> snake2 -> sT ; conv1 -> + x -> raw, snake_next -> sA
   const ConvW& c7 = h->convs.at(pfx + "layers.1.");
   const ConvW& c1 = h->convs.at(pfx + "layers.3.");
   const SnakeW& s2 = h->snakes.at(pfx + "layers.2.");
   typedef EpiConv<BF16> E;
-  typename E::Params e7{c7.bias, nullptr, nullptr, sT, s2.a, s2.ib, C, L, 1, 0};
-  SATB_PROPAGATE((run_conv_gemm<E, BF16>(h, c7, sA, B, L, 0, dil, 1, e7, st)));
   typename E::Params e1{c1.bias, raw, keep_raw ? raw : nullptr, sA, next_snake ? next_snake->a : nullptr,
                         next_snake ? next_snake->ib : nullptr, C, L, 1, 0};
+  if (C == ResUnitCfg::kC && c7.k == ResUnitCfg::kTaps && L >= 512 && gemm_use_2cta() && resunit_use_fused()) {
+    // one kernel: conv7 -> snake2 -> conv1 -> + skip; reads sA (with a halo), so it must write elsewhere
+    const CUtensorMap *ta, *tb7, *tb1;
+    SATB_PROPAGATE(get_tmap_a(h, sA, C, L, B, L, 1, &ta));
+    SATB_PROPAGATE(get_tmap_b(h, c7, c7.k * C, 64, &tb7));
+    SATB_PROPAGATE(get_tmap_b(h, c1, C, 64, &tb1));
+    e1.s16_out = sT;
+    ResUnitParams<BF16> rp{c7.bias, s2.a, s2.ib, e1};
+    ResUnitShape rs{L, B, dil};
+    SATB_PROPAGATE(launch_resunit<BF16>(*ta, *tb7, *tb1, rs, rp, st));
+    std::swap(sA, sT);
+    return 0;
+  }
+  // conv7(dil) on sA -> snake2 -> sT ; conv1 on sT -> + x -> raw, snake_next -> sA
+  typename E::Params e7{c7.bias, nullptr, nullptr, sT, s2.a, s2.ib, C, L, 1, 0};
+  SATB_PROPAGATE((run_conv_gemm<E, BF16>(h, c7, sA, B, L, 0, dil, 1, e7, st)));
   SATB_PROPAGATE((run_conv_gemm<E, BF16>(h, c1, sT, B, L, 0, 1, 1, e1, st)));
   return 0;
 }

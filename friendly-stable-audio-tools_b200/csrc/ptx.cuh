@@ -239,6 +239,29 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       : "memory");
 }
 
+// Same with release semantics at cluster scope: publishes this thread's prior shared-memory writes
+// (after a fence.proxy.async) to the CTA that waits with mbar_wait_cluster.
+__device__ __forceinline__ void mbar_arrive_remote_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendHintNs)
+        : "memory");
+  } while (!ok);
+}
+
 // Shared-memory matrix descriptor, K-major operand stored as rows of 64 16-bit
 // elements (128 B) with the 128-byte swizzle TMA produces (CU_TENSOR_MAP_SWIZZLE_128B):
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (unused for swizzled K-major)

@@ -1,0 +1,314 @@
+// Fused Oobleck ResidualUnit for 128-channel stages (models/autoencoders.py:45-68):
+//
+//   y = x + conv1x1( snake2( conv7_dilated( snake1(x) ) ) )
+//
+// One kernel per unit.  The k7 convolution runs as a 7-tap implicit GEMM exactly like
+// gemm_tcgen05_2cta_kernel (CTA pair, 256 positions x 128 channels per tile); its fp32
+// accumulator never leaves the SM: the epilogue warps add the bias, apply snake2, round to
+// the 16-bit operand type and write the tile into shared memory in the 128B-swizzled K-major
+// layout, from where a second tcgen05 GEMM (K = 128, the 1x1 convolution, weights resident in
+// smem) produces the unit's output in a second TMEM accumulator.  Its epilogue is EpiConv:
+// + bias + fp32 skip, fp32 raw stream out, and the consumer's Snake fused into the 16-bit copy.
+// Compared with two launches this removes one 16-bit write + read of the whole activation and
+// one full pass of launch/fill/drain per unit.
+//
+// Pipeline per CTA pair (tile t):  tensor pipe  conv7(t) -> G2(t-1) -> conv7(t+1) -> G2(t) ...
+//                                  epilogue     A(t) [acc1 -> smem]   B(t-1) [acc2 -> HBM] ...
+// TMEM: acc1 double-buffered at columns [0,256), acc2 double-buffered at [256,512).
+#pragma once
+#include "gemm.cuh"
+
+namespace satb {
+
+struct ResUnitShape {
+  int L;        // positions per batch item
+  int batches;
+  int dil;      // dilation of the k7 convolution
+};
+
+template <bool BF16>
+struct ResUnitParams {
+  const float* bias7;    // [128]
+  const float* sn2_a;    // inner Snake: e^alpha
+  const float* sn2_ib;   // inner Snake: 1/(e^beta + 1e-9)
+  typename EpiConv<BF16>::Params out;   // 1x1-conv epilogue (bias, skip, raw out, 16-bit out + next Snake)
+};
+
+struct ResUnitCfg {
+  static constexpr int kC = 128;
+  static constexpr int kTaps = 7;
+  static constexpr int kStageA = kBlockM * kBlockK * 2;      // 16 KB: 128 positions x 64 channels
+  static constexpr int kStageB = (kC / 2) * kBlockK * 2;     //  8 KB: this CTA's 64 output channels
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = 5;
+  static constexpr int kA2Bytes = 2 * kStageA;               // snake2(conv7) tile, two 64-channel k-blocks
+  static constexpr int kW1Bytes = 2 * kStageB;               // 1x1 weights of this CTA's 64 output channels
+  static constexpr int kOffA2 = kStages * kStage;
+  static constexpr int kOffW1 = kOffA2 + kA2Bytes;
+  static constexpr int kOffBars = kOffW1 + kW1Bytes;
+  static constexpr int kOffParams = kOffBars + 256;          // bias7 | sn2_a | sn2_ib, 3 x 128 floats
+  static constexpr int kOffEpiStage = kOffParams + 3 * kC * 4;
+  static constexpr int kEpiStage = 32 * 36 * 4;
+  static constexpr int kSmemBytes = kOffEpiStage + kEpiWarps * kEpiStage + 1024;
+  static constexpr int kTmemCols = 512;
+  static_assert(kSmemBytes <= 227 * 1024, "smem budget");
+};
+
+template <bool BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB7,
+                            const __grid_constant__ CUtensorMap tmB1, const ResUnitShape s,
+                            const ResUnitParams<BF16> ep) {
+  using Cfg = ResUnitCfg;
+  using Epi = EpiConv<BF16>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a2s = smem + Cfg::kOffA2;
+  uint8_t* w1s = smem + Cfg::kOffW1;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
+  uint64_t* full_bar = bars;                       // CTA 0 (credited by both CTAs' TMA)
+  uint64_t* empty_bar = bars + Cfg::kStages;       // per CTA, multicast commit
+  uint64_t* acc1_full = empty_bar + Cfg::kStages;  // [2] per CTA, multicast commit
+  uint64_t* a2_full = acc1_full + 2;               // CTA 0, 16 arrivals (8 epilogue warps x 2 CTAs)
+  uint64_t* a2_empty = a2_full + 1;                // per CTA, multicast commit of G2
+  uint64_t* acc2_full = a2_empty + 1;              // [2] per CTA, multicast commit
+  uint64_t* acc2_empty = acc2_full + 2;            // [2] CTA 0, 16 arrivals
+  uint64_t* w1_full = acc2_empty + 2;              // CTA 0
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w1_full + 1);
+  float* prm = reinterpret_cast<float*>(smem + Cfg::kOffParams);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  const int m_tiles = (s.L + 2 * kBlockM - 1) / (2 * kBlockM);
+  const int total_tiles = m_tiles * s.batches;
+  constexpr int kKb = Cfg::kC / kBlockK;          // 2 k-blocks per tap
+  constexpr int kNumKb = kKb * Cfg::kTaps;        // 14 ring stages per tile
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB7);
+    tma_prefetch_desc(&tmB1);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc1_full[i], 1);
+      mbar_init(&acc2_full[i], 1);
+      mbar_init(&acc2_empty[i], 16);
+    }
+    mbar_init(a2_full, 16);
+    mbar_init(a2_empty, 1);
+    mbar_init(w1_full, 1);
+    fence_mbar_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + 3 * 32) {   // 96 threads x float4 = 3 x 128 floats
+    const int i = threadIdx.x - 128;
+    const float* src = i < 32 ? ep.bias7 : (i < 64 ? ep.sn2_a : ep.sn2_ib);
+    reinterpret_cast<float4*>(prm)[i] =
+        src ? __ldg(reinterpret_cast<const float4*>(src) + (i & 31)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ------------------------------------------------------ TMA producer (both CTAs)
+      if (rank == 0) mbar_expect_tx(w1_full, 2 * Cfg::kW1Bytes);
+      for (int kb = 0; kb < kKb; ++kb)
+        tma_load_2d_2sm(w1s + kb * Cfg::kStageB, &tmB1, w1_full, kb * kBlockK, rank * (Cfg::kC / 2));
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        const int batch = tile / m_tiles;
+        const int m0 = (tile - batch * m_tiles) * 2 * kBlockM + rank * kBlockM;
+        for (int kb = 0; kb < kNumKb; ++kb) {
+          const int tap = kb / kKb;
+          const int k0 = (kb - tap * kKb) * kBlockK;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStage;
+          uint8_t* sb = sa + Cfg::kStageA;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStage);
+          tma_load_4d_2sm(sa, &tmA, &full_bar[stage], k0, 0, m0 + (tap - 3) * s.dil, batch);
+          tma_load_2d_2sm(sb, &tmB7, &full_bar[stage], k0, tap * Cfg::kC + rank * (Cfg::kC / 2));
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      // ------------------------------------------------------ MMA issuer (CTA 0 for the pair)
+      constexpr uint32_t idesc = make_idesc_f16(2 * kBlockM, Cfg::kC, BF16);
+      const uint32_t a2_addr = smem_u32(a2s), w1_addr = smem_u32(w1s);
+      auto g2 = [&](int j) {   // 1x1 convolution of tile j: acc2[j & 1] = A2 x W1^T
+        mbar_wait_cluster(a2_full, j & 1);
+        mbar_wait(&acc2_empty[j & 1], ((j >> 1) & 1) ^ 1);
+        if (j == 0) mbar_wait(w1_full, 0);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + 256 + (j & 1) * Cfg::kC;
+#pragma unroll
+        for (int kb = 0; kb < kKb; ++kb) {
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = make_desc_kmajor_sw128(a2_addr + kb * Cfg::kStageA + k * kUmmaK * 2);
+            const uint64_t db = make_desc_kmajor_sw128(w1_addr + kb * Cfg::kStageB + k * kUmmaK * 2);
+            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit_2sm(a2_empty);
+        umma_commit_2sm(&acc2_full[j & 1]);
+      };
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+        // acc1[it & 1] is free: phase A of tile it-2 was observed (a2_full) before G2(it-2) was issued
+        const uint32_t d_tmem = tmem_base + (it & 1) * Cfg::kC;
+        for (int kb = 0; kb < kNumKb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStage);
+          const uint32_t b_addr = a_addr + Cfg::kStageA;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = make_desc_kmajor_sw128(a_addr + k * kUmmaK * 2);
+            const uint64_t db = make_desc_kmajor_sw128(b_addr + k * kUmmaK * 2);
+            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&acc1_full[it & 1]);
+        if (it > 0) g2(it - 1);
+      }
+      if (it > 0) g2(it - 1);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (both CTAs)
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int row = q * 32 + lane;                 // this thread's row of the CTA's 128 positions
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float* stage_buf = reinterpret_cast<float*>(smem + Cfg::kOffEpiStage + (warp - 4) * Cfg::kEpiStage);
+
+    auto phase_a = [&](int it) {   // acc1 -> + bias7 -> snake2 -> 16-bit -> swizzled smem tile
+      mbar_wait(&acc1_full[it & 1], (it >> 1) & 1);
+      if (it > 0) mbar_wait(a2_empty, (it - 1) & 1);   // G2 of the previous tile has consumed the smem tile
+      tc_fence_after();
+      const uint32_t t_row = t_lane + (it & 1) * Cfg::kC;
+      uint32_t r[32];
+#pragma unroll 1
+      for (int ci = half; ci < 4; ci += 2) {
+        tmem_ld_32x32(t_row + ci * 32, r);
+        tmem_ld_wait();
+        uint32_t o[16];
+        const float* pb = prm + ci * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = *reinterpret_cast<const float4*>(pb + 4 * j);
+          const float4 a4 = *reinterpret_cast<const float4*>(pb + Cfg::kC + 4 * j);
+          const float4 i4 = *reinterpret_cast<const float4*>(pb + 2 * Cfg::kC + 4 * j);
+          const float v0 = snake_fast(__uint_as_float(r[4 * j]) + b4.x, a4.x, i4.x);
+          const float v1 = snake_fast(__uint_as_float(r[4 * j + 1]) + b4.y, a4.y, i4.y);
+          const float v2 = snake_fast(__uint_as_float(r[4 * j + 2]) + b4.z, a4.z, i4.z);
+          const float v3 = snake_fast(__uint_as_float(r[4 * j + 3]) + b4.w, a4.w, i4.w);
+          o[2 * j] = Op16<BF16>::pack(v0, v1);
+          o[2 * j + 1] = Op16<BF16>::pack(v2, v3);
+        }
+        uint8_t* rowp = a2s + (ci >> 1) * Cfg::kStageA + row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c16 = ((ci & 1) * 4 + j) ^ (row & 7);
+          *reinterpret_cast<uint4*>(rowp + c16 * 16) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        }
+      }
+      fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core's async proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote_cluster(a2_full, 0);
+    };
+
+    auto phase_b = [&](int j, int batch, int m0) {   // acc2 -> EpiConv (bias, skip, raw, snake_next)
+      mbar_wait(&acc2_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      EpiCtx c;
+      c.l = m0 + row;
+      c.batch = batch;
+      c.row = batch * s.L + c.l;
+      c.valid = c.l < s.L;
+      c.l0 = m0 + q * 32;
+      c.L = s.L;
+      c.lane = lane;
+      c.stage = stage_buf;
+      const uint32_t t_row = t_lane + 256 + (j & 1) * Cfg::kC;
+      uint32_t r[32];
+#pragma unroll 1
+      for (int ci = half; ci < 4; ci += 2) {
+        tmem_ld_32x32(t_row + ci * 32, r);
+        tmem_ld_wait();
+        c.col0 = ci * 32;
+        Epi::apply(ep.out, c, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&acc2_empty[j & 1], 0);
+    };
+
+    int it = 0, prev_batch = 0, prev_m0 = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+      const int batch = tile / m_tiles;
+      const int m0 = (tile - batch * m_tiles) * 2 * kBlockM + rank * kBlockM;
+      phase_a(it);
+      if (it > 0) phase_b(it - 1, prev_batch, prev_m0);
+      prev_batch = batch;
+      prev_m0 = m0;
+    }
+    if (it > 0) phase_b(it - 1, prev_batch, prev_m0);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <bool BF16>
+int launch_resunit(const CUtensorMap& tmA, const CUtensorMap& tmB7, const CUtensorMap& tmB1, const ResUnitShape& s,
+                   const ResUnitParams<BF16>& ep, cudaStream_t stream) {
+  using Cfg = ResUnitCfg;
+  auto kern = resunit_tcgen05_2cta_kernel<BF16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int total = ceil_div(s.L, 2 * kBlockM) * s.batches;
+  if (total <= 0) return 0;
+  int clusters = device_sm_count() / 2;
+  if (clusters > total) clusters = total;
+  SATB_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tmA, tmB7, tmB1, s, ep));
+  count_launch();
+  return 0;
+}
+
+}  // namespace satb

@@ -34,6 +34,15 @@ bool gemm_use_2cta() {
   return v == 1;
 }
 
+bool resunit_use_fused() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SATB_RESUNIT");
+    v = (e && std::string(e) == "unfused") ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int device_sm_count() {
   static int cached = 0;
   if (cached == 0) {

@@ -31,14 +31,40 @@ def snake_beta(x, alpha, beta):
     return x + (1.0 / (b + 0.000000001)) * torch.sin(x * a).pow(2)
 
 
+# Optional emulation of the native path's 16-bit tensor-core operands (tests only): when set to
+# torch.float16 / torch.bfloat16 every convolution rounds its input and its folded weight to that
+# type (the accumulation, biases, Snake and the skip stream stay fp32, like the CUDA kernels).
+# None (default) = the reference's plain fp32 arithmetic.
+_OPERAND_DTYPE = None
+
+
+class operand_rounding:
+    """with operand_rounding(torch.float16): ... -> the oracle rounds conv operands like the GPU path."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global _OPERAND_DTYPE
+        self.prev, _OPERAND_DTYPE = _OPERAND_DTYPE, self.dtype
+
+    def __exit__(self, *exc):
+        global _OPERAND_DTYPE
+        _OPERAND_DTYPE = self.prev
+
+
+def _rnd(t):
+    return t if _OPERAND_DTYPE is None else t.to(_OPERAND_DTYPE).to(t.dtype)
+
+
 def _wn_conv(x, sd, pfx, **kw):
     w = fold_weight_norm(sd[pfx + "weight_g"], sd[pfx + "weight_v"])
-    return F.conv1d(x, w, sd.get(pfx + "bias"), **kw)
+    return F.conv1d(_rnd(x), _rnd(w), sd.get(pfx + "bias"), **kw)
 
 
 def _wn_convT(x, sd, pfx, **kw):
     w = fold_weight_norm(sd[pfx + "weight_g"], sd[pfx + "weight_v"])
-    return F.conv_transpose1d(x, w, sd.get(pfx + "bias"), **kw)
+    return F.conv_transpose1d(_rnd(x), _rnd(w), sd.get(pfx + "bias"), **kw)
 
 
 def residual_unit(x, sd, pfx, dilation):

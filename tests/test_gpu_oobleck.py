@@ -4,7 +4,10 @@ reference modules and against the CPU oracle, through the drop-in modules (ctype
 Tolerance: the native convolutions use fp16 operands with fp32 accumulation and an fp32
 residual stream; the reference (TF32 disabled, inference/generation.py:165-166) is fp32.
 Gate: rel-L2 <= 3e-3 on the decoded audio (~50 dB SNR) for the 3-stage golden model with fp16
-operands (2.5e-2 for bf16); <= 1e-2 through the full 5-stage / 37-convolution SA-Open decoder."""
+operands (2.5e-2 for bf16).  Through the full 5-stage / 37-convolution SA-Open stack with synthetic
+weights the operand rounding itself is amplified to ~1e-2 (every Snake has slope up to 1 + e^alpha/e^beta),
+so those tests measure that floor with the oracle (same fp32 arithmetic, conv operands rounded to fp16:
+oobleck_oracle.operand_rounding) and require the GPU result to be within 2x of it."""
 import json
 
 import pytest
@@ -107,6 +110,49 @@ def test_full_sao_decoder_vs_oracle():
     torch.manual_seed(3)
     z = torch.randn(1, 64, 8)
     ref = oo.oobleck_decoder(z, dsd, dcfg)
+    with oo.operand_rounding(torch.float16):
+        floor = rel_l2(oo.oobleck_decoder(z, dsd, dcfg), ref)
     y = dec.cuda().eval()(z.cuda()).cpu()
     assert y.shape == ref.shape == (1, 2, 8 * 2048)
-    assert rel_l2(y, ref) < 1e-2
+    assert rel_l2(y, ref) < 2.0 * floor, (rel_l2(y, ref), floor)
+
+
+SAO_VAE = dict(channels=128, c_mults=[1, 2, 4, 8, 16], strides=[2, 4, 4, 8, 8], latent_dim=64, use_snake=True)
+
+
+def test_sao_decoder_many_tiles_vs_oracle():
+    """SA-Open decoder, batch 2 x 24 latents: the 128-channel stages run the fused ResidualUnit kernel with
+    several 256-position tiles per CTA pair (accumulator / smem-tile hand-offs wrap around) and a batch edge."""
+    from oracle import oobleck_oracle as oo
+    from stable_audio_tools.models.autoencoders import OobleckDecoder
+    dcfg = dict(SAO_VAE, out_channels=2, final_tanh=False)
+    dsd = oo.make_oobleck_weights(oo.decoder_param_shapes(dcfg), seed=11, transposed=oo.decoder_transposed_prefixes(dcfg))
+    dec = OobleckDecoder(**dcfg)
+    dec.load_state_dict(dsd)
+    torch.manual_seed(4)
+    z = torch.randn(2, 64, 24)
+    ref = oo.oobleck_decoder(z, dsd, dcfg)
+    with oo.operand_rounding(torch.float16):
+        floor = rel_l2(oo.oobleck_decoder(z, dsd, dcfg), ref)
+    y = dec.cuda().eval()(z.cuda()).cpu()
+    assert y.shape == ref.shape == (2, 2, 24 * 2048)
+    assert rel_l2(y, ref) < 2.0 * floor, (rel_l2(y, ref), floor)
+    assert rel_l2(y[1], ref[1]) < 2.0 * floor
+
+
+def test_full_sao_encoder_vs_oracle():
+    """SA-Open encoder (2 -> 128 ... 2048 channels, strides 2,4,4,8,8) on 24 x 2048 samples vs the fp32 oracle."""
+    from oracle import oobleck_oracle as oo
+    from stable_audio_tools.models.autoencoders import OobleckEncoder
+    ecfg = dict(SAO_VAE, in_channels=2, latent_dim=128)
+    esd = oo.make_oobleck_weights(oo.encoder_param_shapes(ecfg), seed=12)
+    enc = OobleckEncoder(**ecfg)
+    enc.load_state_dict(esd)
+    torch.manual_seed(5)
+    a = 0.5 * torch.randn(1, 2, 24 * 2048).clamp(-1, 1)
+    ref = oo.oobleck_encoder(a, esd, ecfg)
+    with oo.operand_rounding(torch.float16):
+        floor = rel_l2(oo.oobleck_encoder(a, esd, ecfg), ref)
+    y = enc.cuda().eval()(a.cuda()).cpu()
+    assert y.shape == ref.shape == (1, 128, 24)
+    assert rel_l2(y, ref) < 2.0 * floor, (rel_l2(y, ref), floor)
