@@ -689,28 +689,42 @@ struct EpiConv {
   // Warp-cooperative: the accumulator chunk (thread = row, 32 columns) is transposed through the
   // per-warp smem tile so that every global access is coalesced (8 lanes x 16 B = one 128 B row
   // segment, 4 rows per instruction) and each lane needs the per-channel parameters of only 4 channels.
-  __device__ static __forceinline__ void apply(const Params& p, const EpiCtx& c, const uint32_t (&r)[32]) {
-    float* st = c.stage;
-    int phase = 0, co0 = c.col0;
+  // Column decomposition of a chunk, computed once: transposed convolutions put (phase, channel) on N.
+  struct Seg {
+    int phase, co;
+  };
+  __device__ static __forceinline__ Seg seg_of(const Params& p, const EpiCtx& c) {
+    Seg sg{0, c.col0};
     if (p.up > 1) {
-      phase = c.col0 / p.cout;
-      co0 = c.col0 - phase * p.cout;
+      sg.phase = c.col0 / p.cout;
+      sg.co = c.col0 - sg.phase * p.cout;
     }
-    const int g = c.lane & 7, r0 = c.lane >> 3;
-    const int co = co0 + 4 * g;
-    // residual (skip) values of this lane's 8 row segments: issued first so that the loads are in
-    // flight during the smem transpose
-    float4 rs[8];
-    size_t idx[8];
-    bool ok[8];
+    sg.co += 4 * (c.lane & 7);
+    return sg;
+  }
+  // Output address of row segment i (rows r0 + 4i of this warp's 32, channels co .. co+3);
+  // false when the row / output position does not exist.
+  __device__ static __forceinline__ bool seg_index(const Params& p, const EpiCtx& c, const Seg& sg, int i, size_t* idx) {
+    const int l = c.l0 + (c.lane >> 3) + 4 * i;
+    const int lo = l * p.up + sg.phase - p.pad;
+    const bool ok = l < c.L && lo >= 0 && lo < p.L_out;
+    *idx = (static_cast<size_t>(c.batch) * p.L_out + (ok ? lo : 0)) * p.cout + sg.co;
+    return ok;
+  }
+  // Issue the residual (skip) loads of a chunk; they can be left in flight across other work.
+  __device__ static __forceinline__ void prefetch(const Params& p, const EpiCtx& c, float4 (&rs)[8]) {
+    const Seg sg = seg_of(p, c);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int l = c.l0 + r0 + 4 * i;
-      const int lo = l * p.up + phase - p.pad;
-      ok[i] = l < c.L && lo >= 0 && lo < p.L_out;
-      idx[i] = (static_cast<size_t>(c.batch) * p.L_out + (ok[i] ? lo : 0)) * p.cout + co;
-      rs[i] = (ok[i] && p.resid) ? *reinterpret_cast<const float4*>(p.resid + idx[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      size_t idx;
+      const bool ok = seg_index(p, c, sg, i, &idx);
+      rs[i] = (ok && p.resid) ? *reinterpret_cast<const float4*>(p.resid + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  }
+  __device__ static __forceinline__ void finish(const Params& p, const EpiCtx& c, const uint32_t (&r)[32],
+                                                const float4 (&rs)[8]) {
+    float* st = c.stage;
+    const int g = c.lane & 7, r0 = c.lane >> 3;
     {
       float4* mine = reinterpret_cast<float4*>(st + c.lane * 36);
 #pragma unroll
@@ -719,6 +733,8 @@ struct EpiConv {
                               __uint_as_float(r[4 * j + 3]));
     }
     __syncwarp();
+    const Seg sg = seg_of(p, c);
+    const int co = sg.co;
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), a4 = b4, ib4 = b4;
     if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
     const bool snake = p.s16_out != nullptr && p.sn_a != nullptr;
@@ -728,10 +744,11 @@ struct EpiConv {
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      if (ok[i]) {
+      size_t idx;
+      if (seg_index(p, c, sg, i, &idx)) {
         float4 v = *reinterpret_cast<const float4*>(st + (r0 + 4 * i) * 36 + 4 * g);
         v.x += b4.x + rs[i].x; v.y += b4.y + rs[i].y; v.z += b4.z + rs[i].z; v.w += b4.w + rs[i].w;
-        if (p.raw_out) *reinterpret_cast<float4*>(p.raw_out + idx[i]) = v;
+        if (p.raw_out) *reinterpret_cast<float4*>(p.raw_out + idx) = v;
         if (p.s16_out) {
           if (snake) {
             v.x = snake_fast(v.x, a4.x, ib4.x);
@@ -739,12 +756,19 @@ struct EpiConv {
             v.z = snake_fast(v.z, a4.z, ib4.z);
             v.w = snake_fast(v.w, a4.w, ib4.w);
           }
-          *reinterpret_cast<uint2*>(static_cast<uint16_t*>(p.s16_out) + idx[i]) =
+          *reinterpret_cast<uint2*>(static_cast<uint16_t*>(p.s16_out) + idx) =
               make_uint2(Op16<BF16>::pack(v.x, v.y), Op16<BF16>::pack(v.z, v.w));
         }
       }
     }
     __syncwarp();
+  }
+  // residual values of this lane's 8 row segments are requested first so that the loads are in
+  // flight during the smem transpose
+  __device__ static __forceinline__ void apply(const Params& p, const EpiCtx& c, const uint32_t (&r)[32]) {
+    float4 rs[8];
+    prefetch(p, c, rs);
+    finish(p, c, r, rs);
   }
 };
 

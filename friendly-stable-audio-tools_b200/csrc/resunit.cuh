@@ -40,7 +40,9 @@ struct ResUnitCfg {
   static constexpr int kStageA = kBlockM * kBlockK * 2;      // 16 KB: 128 positions x 64 channels
   static constexpr int kStageB = (kC / 2) * kBlockK * 2;     //  8 KB: this CTA's 64 output channels
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = 5;
+  static constexpr int kStages = 4;
+  static constexpr int kEpiWarpsRU = 16;                     // 4 per TMEM lane quadrant, one 32-column chunk each
+  static constexpr int kThreads = (4 + kEpiWarpsRU) * 32;
   static constexpr int kA2Bytes = 2 * kStageA;               // snake2(conv7) tile, two 64-channel k-blocks
   static constexpr int kW1Bytes = 2 * kStageB;               // 1x1 weights of this CTA's 64 output channels
   static constexpr int kOffA2 = kStages * kStage;
@@ -49,13 +51,13 @@ struct ResUnitCfg {
   static constexpr int kOffParams = kOffBars + 256;          // bias7 | sn2_a | sn2_ib, 3 x 128 floats
   static constexpr int kOffEpiStage = kOffParams + 3 * kC * 4;
   static constexpr int kEpiStage = 32 * 36 * 4;
-  static constexpr int kSmemBytes = kOffEpiStage + kEpiWarps * kEpiStage + 1024;
+  static constexpr int kSmemBytes = kOffEpiStage + kEpiWarpsRU * kEpiStage + 1024;
   static constexpr int kTmemCols = 512;
   static_assert(kSmemBytes <= 227 * 1024, "smem budget");
 };
 
 template <bool BF16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ResUnitCfg::kThreads, 1)
 resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB7,
                             const __grid_constant__ CUtensorMap tmB1, const ResUnitShape s,
                             const ResUnitParams<BF16> ep) {
@@ -69,10 +71,11 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   uint64_t* full_bar = bars;                       // CTA 0 (credited by both CTAs' TMA)
   uint64_t* empty_bar = bars + Cfg::kStages;       // per CTA, multicast commit
   uint64_t* acc1_full = empty_bar + Cfg::kStages;  // [2] per CTA, multicast commit
-  uint64_t* a2_full = acc1_full + 2;               // CTA 0, 16 arrivals (8 epilogue warps x 2 CTAs)
-  uint64_t* a2_empty = a2_full + 1;                // per CTA, multicast commit of G2
+  uint64_t* a2_full = acc1_full + 2;               // CTA 0, 2 arrivals (one forwarder thread per CTA)
+  uint64_t* a2_local = a2_full + 1;                // per CTA, 16 arrivals (this CTA's epilogue warps)
+  uint64_t* a2_empty = a2_local + 1;               // per CTA, multicast commit of G2
   uint64_t* acc2_full = a2_empty + 1;              // [2] per CTA, multicast commit
-  uint64_t* acc2_empty = acc2_full + 2;            // [2] CTA 0, 16 arrivals
+  uint64_t* acc2_empty = acc2_full + 2;            // [2] CTA 0, 32 arrivals
   uint64_t* w1_full = acc2_empty + 2;              // CTA 0
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w1_full + 1);
   float* prm = reinterpret_cast<float*>(smem + Cfg::kOffParams);
@@ -98,9 +101,10 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc1_full[i], 1);
       mbar_init(&acc2_full[i], 1);
-      mbar_init(&acc2_empty[i], 16);
+      mbar_init(&acc2_empty[i], 2 * Cfg::kEpiWarpsRU);
     }
-    mbar_init(a2_full, 16);
+    mbar_init(a2_full, 2);
+    mbar_init(a2_local, Cfg::kEpiWarpsRU);
     mbar_init(a2_empty, 1);
     mbar_init(w1_full, 1);
     fence_mbar_init();
@@ -116,7 +120,7 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   pdl_wait();
-  if (threadIdx.x >= 128 && threadIdx.x < 128 + 3 * 32) {   // 96 threads x float4 = 3 x 128 floats
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + 3 * 32) {     // 96 threads x float4 = 3 x 128 floats
     const int i = threadIdx.x - 128;
     const float* src = i < 32 ? ep.bias7 : (i < 64 ? ep.sn2_a : ep.sn2_ib);
     reinterpret_cast<float4*>(prm)[i] =
@@ -202,54 +206,60 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       }
       if (it > 0) g2(it - 1);
     }
+  } else if (warp == 3) {
+    if (elect_one()) {
+      // ------------------------------------------------------ forwarder (both CTAs)
+      // The epilogue warps publish their smem tile on a CTA-local barrier; this otherwise idle thread
+      // relays it to the MMA thread in CTA 0 with cluster-scope release semantics, so the expensive
+      // cluster-wide memory barrier is not executed by warps that have global loads/stores in flight.
+      int it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+        mbar_wait(a2_local, it & 1);
+        mbar_arrive_remote_cluster(a2_full, 0);
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (both CTAs)
-    const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int q = warp & 3;                        // TMEM lane quadrant
+    const int ci = (warp - 4) >> 2;                // this warp's 32-column chunk (both phases)
     const int row = q * 32 + lane;                 // this thread's row of the CTA's 128 positions
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ci * 32;
     float* stage_buf = reinterpret_cast<float*>(smem + Cfg::kOffEpiStage + (warp - 4) * Cfg::kEpiStage);
 
     auto phase_a = [&](int it) {   // acc1 -> + bias7 -> snake2 -> 16-bit -> swizzled smem tile
       mbar_wait(&acc1_full[it & 1], (it >> 1) & 1);
-      if (it > 0) mbar_wait(a2_empty, (it - 1) & 1);   // G2 of the previous tile has consumed the smem tile
       tc_fence_after();
-      const uint32_t t_row = t_lane + (it & 1) * Cfg::kC;
       uint32_t r[32];
-#pragma unroll 1
-      for (int ci = half; ci < 4; ci += 2) {
-        tmem_ld_32x32(t_row + ci * 32, r);
-        tmem_ld_wait();
-        uint32_t o[16];
-        const float* pb = prm + ci * 32;
+      tmem_ld_32x32(t_lane + (it & 1) * Cfg::kC, r);
+      if (it > 0) mbar_wait(a2_empty, (it - 1) & 1);   // G2 of the previous tile has consumed the smem tile
+      tmem_ld_wait();
+      uint32_t o[16];
+      const float* pb = prm + ci * 32;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b4 = *reinterpret_cast<const float4*>(pb + 4 * j);
-          const float4 a4 = *reinterpret_cast<const float4*>(pb + Cfg::kC + 4 * j);
-          const float4 i4 = *reinterpret_cast<const float4*>(pb + 2 * Cfg::kC + 4 * j);
-          const float v0 = snake_fast(__uint_as_float(r[4 * j]) + b4.x, a4.x, i4.x);
-          const float v1 = snake_fast(__uint_as_float(r[4 * j + 1]) + b4.y, a4.y, i4.y);
-          const float v2 = snake_fast(__uint_as_float(r[4 * j + 2]) + b4.z, a4.z, i4.z);
-          const float v3 = snake_fast(__uint_as_float(r[4 * j + 3]) + b4.w, a4.w, i4.w);
-          o[2 * j] = Op16<BF16>::pack(v0, v1);
-          o[2 * j + 1] = Op16<BF16>::pack(v2, v3);
-        }
-        uint8_t* rowp = a2s + (ci >> 1) * Cfg::kStageA + row * 128;
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = *reinterpret_cast<const float4*>(pb + 4 * j);
+        const float4 a4 = *reinterpret_cast<const float4*>(pb + Cfg::kC + 4 * j);
+        const float4 i4 = *reinterpret_cast<const float4*>(pb + 2 * Cfg::kC + 4 * j);
+        const float v0 = snake_fast(__uint_as_float(r[4 * j]) + b4.x, a4.x, i4.x);
+        const float v1 = snake_fast(__uint_as_float(r[4 * j + 1]) + b4.y, a4.y, i4.y);
+        const float v2 = snake_fast(__uint_as_float(r[4 * j + 2]) + b4.z, a4.z, i4.z);
+        const float v3 = snake_fast(__uint_as_float(r[4 * j + 3]) + b4.w, a4.w, i4.w);
+        o[2 * j] = Op16<BF16>::pack(v0, v1);
+        o[2 * j + 1] = Op16<BF16>::pack(v2, v3);
+      }
+      uint8_t* rowp = a2s + (ci >> 1) * Cfg::kStageA + row * 128;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c16 = ((ci & 1) * 4 + j) ^ (row & 7);
-          *reinterpret_cast<uint4*>(rowp + c16 * 16) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-        }
+      for (int j = 0; j < 4; ++j) {
+        const int c16 = ((ci & 1) * 4 + j) ^ (row & 7);
+        *reinterpret_cast<uint4*>(rowp + c16 * 16) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
       }
       fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core's async proxy
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote_cluster(a2_full, 0);
+      if (lane == 0) mbar_arrive(a2_local);
     };
 
     auto phase_b = [&](int j, int batch, int m0) {   // acc2 -> EpiConv (bias, skip, raw, snake_next)
-      mbar_wait(&acc2_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
       EpiCtx c;
       c.l = m0 + row;
       c.batch = batch;
@@ -259,18 +269,18 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       c.L = s.L;
       c.lane = lane;
       c.stage = stage_buf;
-      const uint32_t t_row = t_lane + 256 + (j & 1) * Cfg::kC;
+      c.col0 = ci * 32;
+      float4 rs[8];
+      Epi::prefetch(ep.out, c, rs);                  // skip values: in flight while we wait for G2
+      mbar_wait(&acc2_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
       uint32_t r[32];
-#pragma unroll 1
-      for (int ci = half; ci < 4; ci += 2) {
-        tmem_ld_32x32(t_row + ci * 32, r);
-        tmem_ld_wait();
-        c.col0 = ci * 32;
-        Epi::apply(ep.out, c, r);
-      }
+      tmem_ld_32x32(t_lane + 256 + (j & 1) * Cfg::kC, r);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(&acc2_empty[j & 1], 0);
+      if (lane == 0) mbar_arrive_remote(&acc2_empty[j & 1], 0);   // accumulator chunk is in registers
+      Epi::finish(ep.out, c, r, rs);
     };
 
     int it = 0, prev_batch = 0, prev_m0 = 0;
@@ -306,7 +316,7 @@ int launch_resunit(const CUtensorMap& tmA, const CUtensorMap& tmB7, const CUtens
   if (total <= 0) return 0;
   int clusters = device_sm_count() / 2;
   if (clusters > total) clusters = total;
-  SATB_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tmA, tmB7, tmB1, s, ep));
+  SATB_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, tmA, tmB7, tmB1, s, ep));
   count_launch();
   return 0;
 }
