@@ -16,6 +16,7 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
                         int v_cols, int q_col, int k_col, int v_col, int batch, int H, int H_kv, int Nq, int Nk,
                         bool bf16, cudaStream_t stream, unsigned long long* dbg = nullptr);
 bool attention_use_legacy();
+bool conv_halo_enabled();     // SATB_CONV_HALO=off: generic 7-tap loads for the final conv (A/B debugging)
 bool resunit_use_fused();      // SATB_RESUNIT=unfused runs the 128-channel ResidualUnits as two GEMM launches (A/B debugging)
 bool gemm_use_2cta();          // SATB_GEMM=1cta disables the CTA-pair GEMM (A/B debugging)   // SATB_ATTN=mma selects the round-1 mma.sync kernel (debug only)
 

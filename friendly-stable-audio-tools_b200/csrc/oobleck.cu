@@ -22,6 +22,7 @@
 #include "../../include/satb200.h"
 #include "common.cuh"
 #include "resunit.cuh"
+#include "conv_halo.cuh"
 #include "kernels.h"
 
 namespace satb {
@@ -275,12 +276,14 @@ int prep_snake(SatbOobleck* h, const std::string& pfx, int c, cudaStream_t st) {
   return 0;
 }
 
-int get_tmap_a(SatbOobleck* h, const void* in16, int cin, int a_rows, int B, int L_in, int a_stride, const CUtensorMap** out) {
-  auto key = std::make_tuple(in16, cin, a_rows, B, static_cast<int64_t>(cin), static_cast<int64_t>(L_in) * cin, a_stride);
+int get_tmap_a(SatbOobleck* h, const void* in16, int cin, int a_rows, int B, int L_in, int a_stride, const CUtensorMap** out,
+               int box_rows = kBlockM) {
+  auto key = std::make_tuple(in16, cin, a_rows, B, static_cast<int64_t>(cin), static_cast<int64_t>(L_in) * cin,
+                             a_stride | (box_rows << 8));
   auto it = h->tmaps.find(key);
   if (it == h->tmaps.end()) {
     CUtensorMap m;
-    SATB_PROPAGATE(make_tmap_a(&m, in16, cin, a_rows, B, cin, static_cast<int64_t>(L_in) * cin, a_stride));
+    SATB_PROPAGATE(make_tmap_a(&m, in16, cin, a_rows, B, cin, static_cast<int64_t>(L_in) * cin, a_stride, box_rows));
     it = h->tmaps.emplace(key, m).first;
   }
   *out = &it->second;
@@ -357,10 +360,11 @@ int residual_unit(SatbOobleck* h, const std::string& pfx, int C, int B, int L, i
   typedef EpiConv<BF16> E;
   typename E::Params e1{c1.bias, raw, keep_raw ? raw : nullptr, sA, next_snake ? next_snake->a : nullptr,
                         next_snake ? next_snake->ib : nullptr, C, L, 1, 0};
-  if (C == ResUnitCfg::kC && c7.k == ResUnitCfg::kTaps && L >= 512 && gemm_use_2cta() && resunit_use_fused()) {
+  if (C == ResUnitCfg::kC && c7.k == ResUnitCfg::kTaps && dil <= ResUnitCfg::kMaxDil && L >= 512 && gemm_use_2cta() &&
+      resunit_use_fused()) {
     // one kernel: conv7 -> snake2 -> conv1 -> + skip; reads sA (with a halo), so it must write elsewhere
     const CUtensorMap *ta, *tb7, *tb1;
-    SATB_PROPAGATE(get_tmap_a(h, sA, C, L, B, L, 1, &ta));
+    SATB_PROPAGATE(get_tmap_a(h, sA, C, L, B, L, 1, &ta, ResUnitCfg::halo_rows(dil)));   // one halo box per k-block
     SATB_PROPAGATE(get_tmap_b(h, c7, c7.k * C, 64, &tb7));
     SATB_PROPAGATE(get_tmap_b(h, c1, C, 64, &tb1));
     e1.s16_out = sT;
@@ -444,7 +448,17 @@ int decode_impl(SatbOobleck* h, const float* z, float* audio, int B, int L, cuda
   {
     const ConvW& cf = h->convs.at("layers." + std::to_string(n + 2) + ".");
     EpiStoreNCL::Params ep{audio, nullptr, cf.cout, static_cast<int>(Lc), c.final_tanh};
-    SATB_PROPAGATE((run_conv_gemm<EpiStoreNCL, BF16>(h, cf, sA, B, static_cast<int>(Lc), 0, 1, 1, ep, st)));
+    ConvHaloShape hs{static_cast<int>(Lc), B, cf.cin, cf.k, 1, cf.cout};
+    if (conv_halo_enabled() && cf.cout <= ConvHaloCfg::kBN && cf.cin % kBlockK == 0 && cf.cin <= 256 &&
+        ConvHaloCfg::halo_rows(hs) <= 256) {
+      // every activation row is fetched once per tile instead of once per tap (see conv_halo.cuh)
+      const CUtensorMap *ta, *tb;
+      SATB_PROPAGATE(get_tmap_a(h, sA, cf.cin, static_cast<int>(Lc), B, static_cast<int>(Lc), 1, &ta, ConvHaloCfg::halo_rows(hs)));
+      SATB_PROPAGATE(get_tmap_b(h, cf, cf.k * cf.cout, ConvHaloCfg::kBN, &tb));
+      SATB_PROPAGATE((launch_conv_halo<EpiStoreNCL, BF16>(*ta, *tb, hs, ep, st)));
+    } else {
+      SATB_PROPAGATE((run_conv_gemm<EpiStoreNCL, BF16>(h, cf, sA, B, static_cast<int>(Lc), 0, 1, 1, ep, st)));
+    }
   }
   SATB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -2,19 +2,24 @@
 //
 //   y = x + conv1x1( snake2( conv7_dilated( snake1(x) ) ) )
 //
-// One kernel per unit.  The k7 convolution runs as a 7-tap implicit GEMM exactly like
-// gemm_tcgen05_2cta_kernel (CTA pair, 256 positions x 128 channels per tile); its fp32
-// accumulator never leaves the SM: the epilogue warps add the bias, apply snake2, round to
-// the 16-bit operand type and write the tile into shared memory in the 128B-swizzled K-major
-// layout, from where a second tcgen05 GEMM (K = 128, the 1x1 convolution, weights resident in
-// smem) produces the unit's output in a second TMEM accumulator.  Its epilogue is EpiConv:
-// + bias + fp32 skip, fp32 raw stream out, and the consumer's Snake fused into the 16-bit copy.
-// Compared with two launches this removes one 16-bit write + read of the whole activation and
-// one full pass of launch/fill/drain per unit.
+// One kernel per unit, one CTA pair (tcgen05 cta_group::2) per 256 positions x 128 channels tile.
+//
+//  * k7 convolution = 7-tap implicit GEMM whose A operand is loaded ONCE per tile: TMA brings the
+//    128 + 6*dilation activation rows of a 64-channel k-block into a 128B-swizzled smem slot and tap t
+//    reads it through a matrix descriptor whose start address is shifted by t*dilation rows (the
+//    swizzle is a function of absolute smem address bits, see conv_halo.cuh).  Only the tap weights
+//    stream per tile (8 KB per (tap, k-block) and CTA).  L2 -> SM traffic per tile and CTA drops from
+//    343 KB (A reloaded per tap) to 161 KB, which is what bounded the two-launch version.
+//  * Its fp32 accumulator never leaves the SM: the epilogue warps add the bias, apply snake2, round to
+//    the 16-bit operand type and write the tile to smem in the swizzled K-major layout; a second
+//    tcgen05 GEMM (K = 128, the 1x1 convolution, weights resident) produces the unit's output in a
+//    second TMEM accumulator, whose epilogue is EpiConv: + bias + fp32 skip, fp32 raw stream out, and
+//    the consumer's Snake fused into the 16-bit copy.
 //
 // Pipeline per CTA pair (tile t):  tensor pipe  conv7(t) -> G2(t-1) -> conv7(t+1) -> G2(t) ...
 //                                  epilogue     A(t) [acc1 -> smem]   B(t-1) [acc2 -> HBM] ...
 // TMEM: acc1 double-buffered at columns [0,256), acc2 double-buffered at [256,512).
+// Warps: 0 TMA producer, 1 MMA issuer (CTA 0), 2 TMEM allocator, 3 forwarder, 4-11 epilogue.
 #pragma once
 #include "gemm.cuh"
 
@@ -23,7 +28,7 @@ namespace satb {
 struct ResUnitShape {
   int L;        // positions per batch item
   int batches;
-  int dil;      // dilation of the k7 convolution
+  int dil;      // dilation of the k7 convolution (halo = 6 * dil rows, <= 54)
 };
 
 template <bool BF16>
@@ -37,27 +42,28 @@ struct ResUnitParams {
 struct ResUnitCfg {
   static constexpr int kC = 128;
   static constexpr int kTaps = 7;
-  static constexpr int kStageA = kBlockM * kBlockK * 2;      // 16 KB: 128 positions x 64 channels
-  static constexpr int kStageB = (kC / 2) * kBlockK * 2;     //  8 KB: this CTA's 64 output channels
-  static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = 4;
-  static constexpr int kEpiWarpsRU = 16;                     // 4 per TMEM lane quadrant, one 32-column chunk each
-  static constexpr int kThreads = (4 + kEpiWarpsRU) * 32;
-  static constexpr int kA2Bytes = 2 * kStageA;               // snake2(conv7) tile, two 64-channel k-blocks
-  static constexpr int kW1Bytes = 2 * kStageB;               // 1x1 weights of this CTA's 64 output channels
-  static constexpr int kOffA2 = kStages * kStage;
-  static constexpr int kOffW1 = kOffA2 + kA2Bytes;
-  static constexpr int kOffBars = kOffW1 + kW1Bytes;
-  static constexpr int kOffParams = kOffBars + 256;          // bias7 | sn2_a | sn2_ib, 3 x 128 floats
+  static constexpr int kMaxDil = 9;
+  static constexpr int kKb = kC / kBlockK;                                        // 2 k-blocks of 64 channels
+  static constexpr int kSlotA = ((kBlockM + (kTaps - 1) * kMaxDil) * 128 + 1023) / 1024 * 1024;   // 24 KB halo tile
+  static constexpr int kStagesA = 3;
+  static constexpr int kTileB = (kC / 2) * kBlockK * 2;      // 8 KB: this CTA's 64 output channels of one (tap, k-block)
+  static constexpr int kStagesB = 8;
+  static constexpr int kTileA2 = kBlockM * kBlockK * 2;      // 16 KB per k-block of the snake2(conv7) tile
+  static constexpr int kOffB = kStagesA * kSlotA;
+  static constexpr int kOffA2 = kOffB + kStagesB * kTileB;
+  static constexpr int kOffW1 = kOffA2 + kKb * kTileA2;
+  static constexpr int kOffBars = kOffW1 + kKb * kTileB;
+  static constexpr int kOffParams = kOffBars + 512;          // bias7 | sn2_a | sn2_ib, 3 x 128 floats
   static constexpr int kOffEpiStage = kOffParams + 3 * kC * 4;
   static constexpr int kEpiStage = 32 * 36 * 4;
-  static constexpr int kSmemBytes = kOffEpiStage + kEpiWarpsRU * kEpiStage + 1024;
+  static constexpr int kSmemBytes = kOffEpiStage + kEpiWarps * kEpiStage + 1024;
   static constexpr int kTmemCols = 512;
   static_assert(kSmemBytes <= 227 * 1024, "smem budget");
+  __host__ __device__ static int halo_rows(int dil) { return kBlockM + (kTaps - 1) * dil; }
 };
 
 template <bool BF16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ResUnitCfg::kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB7,
                             const __grid_constant__ CUtensorMap tmB1, const ResUnitShape s,
                             const ResUnitParams<BF16> ep) {
@@ -65,18 +71,21 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   using Epi = EpiConv<BF16>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bs = smem + Cfg::kOffB;
   uint8_t* a2s = smem + Cfg::kOffA2;
   uint8_t* w1s = smem + Cfg::kOffW1;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
-  uint64_t* full_bar = bars;                       // CTA 0 (credited by both CTAs' TMA)
-  uint64_t* empty_bar = bars + Cfg::kStages;       // per CTA, multicast commit
-  uint64_t* acc1_full = empty_bar + Cfg::kStages;  // [2] per CTA, multicast commit
-  uint64_t* a2_full = acc1_full + 2;               // CTA 0, 2 arrivals (one forwarder thread per CTA)
-  uint64_t* a2_local = a2_full + 1;                // per CTA, 16 arrivals (this CTA's epilogue warps)
-  uint64_t* a2_empty = a2_local + 1;               // per CTA, multicast commit of G2
-  uint64_t* acc2_full = a2_empty + 1;              // [2] per CTA, multicast commit
-  uint64_t* acc2_empty = acc2_full + 2;            // [2] CTA 0, 32 arrivals
-  uint64_t* w1_full = acc2_empty + 2;              // CTA 0
+  uint64_t* a_full = bars;                           // [3] CTA 0 (credited by both CTAs' TMA)
+  uint64_t* a_empty = a_full + Cfg::kStagesA;        // [3] per CTA, multicast commit
+  uint64_t* b_full = a_empty + Cfg::kStagesA;        // [8] CTA 0
+  uint64_t* b_empty = b_full + Cfg::kStagesB;        // [8] per CTA, multicast commit
+  uint64_t* acc1_full = b_empty + Cfg::kStagesB;     // [2] per CTA, multicast commit
+  uint64_t* a2_full = acc1_full + 2;                 // CTA 0, 2 arrivals (one forwarder thread per CTA)
+  uint64_t* a2_local = a2_full + 1;                  // per CTA, 8 arrivals (this CTA's epilogue warps)
+  uint64_t* a2_empty = a2_local + 1;                 // per CTA, multicast commit of G2
+  uint64_t* acc2_full = a2_empty + 1;                // [2] per CTA, multicast commit
+  uint64_t* acc2_empty = acc2_full + 2;              // [2] CTA 0, 16 arrivals
+  uint64_t* w1_full = acc2_empty + 2;                // CTA 0
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w1_full + 1);
   float* prm = reinterpret_cast<float*>(smem + Cfg::kOffParams);
 
@@ -87,24 +96,26 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 
   const int m_tiles = (s.L + 2 * kBlockM - 1) / (2 * kBlockM);
   const int total_tiles = m_tiles * s.batches;
-  constexpr int kKb = Cfg::kC / kBlockK;          // 2 k-blocks per tap
-  constexpr int kNumKb = kKb * Cfg::kTaps;        // 14 ring stages per tile
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB7);
     tma_prefetch_desc(&tmB1);
-    for (int i = 0; i < Cfg::kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+    for (int i = 0; i < Cfg::kStagesA; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < Cfg::kStagesB; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc1_full[i], 1);
       mbar_init(&acc2_full[i], 1);
-      mbar_init(&acc2_empty[i], 2 * Cfg::kEpiWarpsRU);
+      mbar_init(&acc2_empty[i], 2 * kEpiWarps);
     }
     mbar_init(a2_full, 2);
-    mbar_init(a2_local, Cfg::kEpiWarpsRU);
+    mbar_init(a2_local, kEpiWarps);
     mbar_init(a2_empty, 1);
     mbar_init(w1_full, 1);
     fence_mbar_init();
@@ -131,26 +142,31 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   if (warp == 0) {
     if (elect_one()) {
       // ------------------------------------------------------ TMA producer (both CTAs)
-      if (rank == 0) mbar_expect_tx(w1_full, 2 * Cfg::kW1Bytes);
-      for (int kb = 0; kb < kKb; ++kb)
-        tma_load_2d_2sm(w1s + kb * Cfg::kStageB, &tmB1, w1_full, kb * kBlockK, rank * (Cfg::kC / 2));
-      int stage = 0;
-      uint32_t phase = 0;
+      if (rank == 0) mbar_expect_tx(w1_full, 2 * Cfg::kKb * Cfg::kTileB);
+      for (int kb = 0; kb < Cfg::kKb; ++kb)
+        tma_load_2d_2sm(w1s + kb * Cfg::kTileB, &tmB1, w1_full, kb * kBlockK, rank * (Cfg::kC / 2));
+      const int a_tx = Cfg::halo_rows(s.dil) * 128;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
         const int batch = tile / m_tiles;
         const int m0 = (tile - batch * m_tiles) * 2 * kBlockM + rank * kBlockM;
-        for (int kb = 0; kb < kNumKb; ++kb) {
-          const int tap = kb / kKb;
-          const int k0 = (kb - tap * kKb) * kBlockK;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::kStage;
-          uint8_t* sb = sa + Cfg::kStageA;
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStage);
-          tma_load_4d_2sm(sa, &tmA, &full_bar[stage], k0, 0, m0 + (tap - 3) * s.dil, batch);
-          tma_load_2d_2sm(sb, &tmB7, &full_bar[stage], k0, tap * Cfg::kC + rank * (Cfg::kC / 2));
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1;
+        for (int kb = 0; kb < Cfg::kKb; ++kb) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          if (rank == 0) mbar_expect_tx(&a_full[sa], 2 * a_tx);
+          tma_load_4d_2sm(smem + sa * Cfg::kSlotA, &tmA, &a_full[sa], kb * kBlockK, 0, m0 - 3 * s.dil, batch);
+          if (++sa == Cfg::kStagesA) {
+            sa = 0;
+            pa ^= 1;
+          }
+          for (int tap = 0; tap < Cfg::kTaps; ++tap) {
+            mbar_wait(&b_empty[sb], pb ^ 1);
+            if (rank == 0) mbar_expect_tx(&b_full[sb], 2 * Cfg::kTileB);
+            tma_load_2d_2sm(bs + sb * Cfg::kTileB, &tmB7, &b_full[sb], kb * kBlockK, tap * Cfg::kC + rank * (Cfg::kC / 2));
+            if (++sb == Cfg::kStagesB) {
+              sb = 0;
+              pb ^= 1;
+            }
           }
         }
       }
@@ -159,7 +175,7 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     if (rank == 0 && elect_one()) {
       // ------------------------------------------------------ MMA issuer (CTA 0 for the pair)
       constexpr uint32_t idesc = make_idesc_f16(2 * kBlockM, Cfg::kC, BF16);
-      const uint32_t a2_addr = smem_u32(a2s), w1_addr = smem_u32(w1s);
+      const uint32_t a2_addr = smem_u32(a2s), w1_addr = smem_u32(w1s), b_addr0 = smem_u32(bs);
       auto g2 = [&](int j) {   // 1x1 convolution of tile j: acc2[j & 1] = A2 x W1^T
         mbar_wait_cluster(a2_full, j & 1);
         mbar_wait(&acc2_empty[j & 1], ((j >> 1) & 1) ^ 1);
@@ -167,38 +183,48 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + 256 + (j & 1) * Cfg::kC;
 #pragma unroll
-        for (int kb = 0; kb < kKb; ++kb) {
+        for (int kb = 0; kb < Cfg::kKb; ++kb) {
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t da = make_desc_kmajor_sw128(a2_addr + kb * Cfg::kStageA + k * kUmmaK * 2);
-            const uint64_t db = make_desc_kmajor_sw128(w1_addr + kb * Cfg::kStageB + k * kUmmaK * 2);
+            const uint64_t da = make_desc_kmajor_sw128(a2_addr + kb * Cfg::kTileA2 + k * kUmmaK * 2);
+            const uint64_t db = make_desc_kmajor_sw128(w1_addr + kb * Cfg::kTileB + k * kUmmaK * 2);
             umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit_2sm(a2_empty);
         umma_commit_2sm(&acc2_full[j & 1]);
       };
-      int stage = 0;
-      uint32_t phase = 0;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
       int it = 0;
+      const uint32_t tap_bytes = s.dil * 128;
       for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
         // acc1[it & 1] is free: phase A of tile it-2 was observed (a2_full) before G2(it-2) was issued
         const uint32_t d_tmem = tmem_base + (it & 1) * Cfg::kC;
-        for (int kb = 0; kb < kNumKb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStage);
-          const uint32_t b_addr = a_addr + Cfg::kStageA;
+        for (int kb = 0; kb < Cfg::kKb; ++kb) {
+          mbar_wait(&a_full[sa], pa);
+          const uint32_t a_addr = smem_u32(smem + sa * Cfg::kSlotA);
+          for (int tap = 0; tap < Cfg::kTaps; ++tap) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint32_t a_tap = a_addr + tap * tap_bytes;     // row-shifted view of the halo tile
+            const uint32_t b_addr = b_addr0 + sb * Cfg::kTileB;
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t da = make_desc_kmajor_sw128(a_addr + k * kUmmaK * 2);
-            const uint64_t db = make_desc_kmajor_sw128(b_addr + k * kUmmaK * 2);
-            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint64_t da = make_desc_kmajor_sw128(a_tap + k * kUmmaK * 2);
+              const uint64_t db = make_desc_kmajor_sw128(b_addr + k * kUmmaK * 2);
+              umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb | tap | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2sm(&b_empty[sb]);
+            if (++sb == Cfg::kStagesB) {
+              sb = 0;
+              pb ^= 1;
+            }
           }
-          umma_commit_2sm(&empty_bar[stage]);
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1;
+          umma_commit_2sm(&a_empty[sa]);
+          if (++sa == Cfg::kStagesA) {
+            sa = 0;
+            pa ^= 1;
           }
         }
         umma_commit_2sm(&acc1_full[it & 1]);
@@ -221,45 +247,51 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (both CTAs)
     const int q = warp & 3;                        // TMEM lane quadrant
-    const int ci = (warp - 4) >> 2;                // this warp's 32-column chunk (both phases)
+    const int half = (warp - 4) >> 2;              // two warps per quadrant: 32-column chunks half, half + 2
     const int row = q * 32 + lane;                 // this thread's row of the CTA's 128 positions
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ci * 32;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float* stage_buf = reinterpret_cast<float*>(smem + Cfg::kOffEpiStage + (warp - 4) * Cfg::kEpiStage);
 
     auto phase_a = [&](int it) {   // acc1 -> + bias7 -> snake2 -> 16-bit -> swizzled smem tile
       mbar_wait(&acc1_full[it & 1], (it >> 1) & 1);
       tc_fence_after();
-      uint32_t r[32];
-      tmem_ld_32x32(t_lane + (it & 1) * Cfg::kC, r);
+      const uint32_t t_row = t_lane + (it & 1) * Cfg::kC;
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(t_row + half * 32, ra);
+      tmem_ld_32x32(t_row + (half + 2) * 32, rb);
       if (it > 0) mbar_wait(a2_empty, (it - 1) & 1);   // G2 of the previous tile has consumed the smem tile
       tmem_ld_wait();
-      uint32_t o[16];
-      const float* pb = prm + ci * 32;
+      auto chunk = [&](int ci, const uint32_t (&r)[32]) {
+        uint32_t o[16];
+        const float* pb = prm + ci * 32;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b4 = *reinterpret_cast<const float4*>(pb + 4 * j);
-        const float4 a4 = *reinterpret_cast<const float4*>(pb + Cfg::kC + 4 * j);
-        const float4 i4 = *reinterpret_cast<const float4*>(pb + 2 * Cfg::kC + 4 * j);
-        const float v0 = snake_fast(__uint_as_float(r[4 * j]) + b4.x, a4.x, i4.x);
-        const float v1 = snake_fast(__uint_as_float(r[4 * j + 1]) + b4.y, a4.y, i4.y);
-        const float v2 = snake_fast(__uint_as_float(r[4 * j + 2]) + b4.z, a4.z, i4.z);
-        const float v3 = snake_fast(__uint_as_float(r[4 * j + 3]) + b4.w, a4.w, i4.w);
-        o[2 * j] = Op16<BF16>::pack(v0, v1);
-        o[2 * j + 1] = Op16<BF16>::pack(v2, v3);
-      }
-      uint8_t* rowp = a2s + (ci >> 1) * Cfg::kStageA + row * 128;
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = *reinterpret_cast<const float4*>(pb + 4 * j);
+          const float4 a4 = *reinterpret_cast<const float4*>(pb + Cfg::kC + 4 * j);
+          const float4 i4 = *reinterpret_cast<const float4*>(pb + 2 * Cfg::kC + 4 * j);
+          const float v0 = snake_fast(__uint_as_float(r[4 * j]) + b4.x, a4.x, i4.x);
+          const float v1 = snake_fast(__uint_as_float(r[4 * j + 1]) + b4.y, a4.y, i4.y);
+          const float v2 = snake_fast(__uint_as_float(r[4 * j + 2]) + b4.z, a4.z, i4.z);
+          const float v3 = snake_fast(__uint_as_float(r[4 * j + 3]) + b4.w, a4.w, i4.w);
+          o[2 * j] = Op16<BF16>::pack(v0, v1);
+          o[2 * j + 1] = Op16<BF16>::pack(v2, v3);
+        }
+        uint8_t* rowp = a2s + (ci >> 1) * Cfg::kTileA2 + row * 128;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c16 = ((ci & 1) * 4 + j) ^ (row & 7);
-        *reinterpret_cast<uint4*>(rowp + c16 * 16) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-      }
+        for (int j = 0; j < 4; ++j) {
+          const int c16 = ((ci & 1) * 4 + j) ^ (row & 7);
+          *reinterpret_cast<uint4*>(rowp + c16 * 16) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        }
+      };
+      chunk(half, ra);
+      chunk(half + 2, rb);
       fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core's async proxy
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(a2_local);
     };
 
-    auto phase_b = [&](int j, int batch, int m0) {   // acc2 -> EpiConv (bias, skip, raw, snake_next)
+    auto make_ctx = [&](int batch, int m0, int ci) {
       EpiCtx c;
       c.l = m0 + row;
       c.batch = batch;
@@ -270,17 +302,26 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       c.lane = lane;
       c.stage = stage_buf;
       c.col0 = ci * 32;
-      float4 rs[8];
-      Epi::prefetch(ep.out, c, rs);                  // skip values: in flight while we wait for G2
+      return c;
+    };
+    auto phase_b = [&](int j, int batch, int m0) {   // acc2 -> EpiConv (bias, skip, raw, snake_next)
+      const EpiCtx c0 = make_ctx(batch, m0, half), c1 = make_ctx(batch, m0, half + 2);
+      float4 rs0[8], rs1[8];
+      Epi::prefetch(ep.out, c0, rs0);                // skip values: in flight while we wait for G2
       mbar_wait(&acc2_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
+      const uint32_t t_row = t_lane + 256 + (j & 1) * Cfg::kC;
       uint32_t r[32];
-      tmem_ld_32x32(t_lane + 256 + (j & 1) * Cfg::kC, r);
+      tmem_ld_32x32(t_row + half * 32, r);
+      Epi::prefetch(ep.out, c1, rs1);
+      tmem_ld_wait();
+      Epi::finish(ep.out, c0, r, rs0);
+      tmem_ld_32x32(t_row + (half + 2) * 32, r);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(&acc2_empty[j & 1], 0);   // accumulator chunk is in registers
-      Epi::finish(ep.out, c, r, rs);
+      if (lane == 0) mbar_arrive_remote(&acc2_empty[j & 1], 0);   // accumulator fully in registers
+      Epi::finish(ep.out, c1, r, rs1);
     };
 
     int it = 0, prev_batch = 0, prev_m0 = 0;
@@ -302,10 +343,12 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   }
 }
 
+// tmA must be built with box rows = ResUnitCfg::halo_rows(s.dil); tmB7 / tmB1 with 64-row boxes.
 template <bool BF16>
 int launch_resunit(const CUtensorMap& tmA, const CUtensorMap& tmB7, const CUtensorMap& tmB1, const ResUnitShape& s,
                    const ResUnitParams<BF16>& ep, cudaStream_t stream) {
   using Cfg = ResUnitCfg;
+  SATB_REQUIRE(s.dil >= 1 && s.dil <= Cfg::kMaxDil, "resunit: dilation out of range");
   auto kern = resunit_tcgen05_2cta_kernel<BF16>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -316,7 +359,7 @@ int launch_resunit(const CUtensorMap& tmA, const CUtensorMap& tmB7, const CUtens
   if (total <= 0) return 0;
   int clusters = device_sm_count() / 2;
   if (clusters > total) clusters = total;
-  SATB_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, tmA, tmB7, tmB1, s, ep));
+  SATB_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tmA, tmB7, tmB1, s, ep));
   count_launch();
   return 0;
 }

@@ -34,6 +34,15 @@ bool gemm_use_2cta() {
   return v == 1;
 }
 
+bool conv_halo_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SATB_CONV_HALO");   // "off": generic per-tap loads (A/B debugging)
+    v = (e && std::string(e) == "off") ? 0 : 1;
+  }
+  return v == 1;
+}
+
 bool resunit_use_fused() {
   static int v = -1;
   if (v < 0) {
