@@ -179,7 +179,9 @@ t = torch.tensor([float(r + 1)])
 td.all_reduce(t, op=td.ReduceOp.MAX)
 assert t.item() == w
 td.destroy_process_group()
-print('rank', r, 'ok')
+import sys
+sys.stdout.write('rank %d ok' % r + chr(10))   # one write per rank: the two ranks share the pipe
+sys.stdout.flush()
 """)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
