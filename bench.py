@@ -394,7 +394,8 @@ def run_native(args):
         decode_ms = float(tmax.item())
     # Oobleck decoder roofline bookkeeping, per sample of L = 1024 latents:
     #   FLOPs 5.163e12; bytes for the fusion level implemented (16-bit activated copy in/out of every
-    #   tensor-core conv, fp32 raw skip stream read+written once per ResidualUnit):
+    #   tensor-core conv, fp32 raw skip stream read+written once per ResidualUnit, the 128-channel
+    #   ResidualUnits fused into one kernel):
     dec_flops = 5.163e12
     dec_bytes = 0.0
     l_out, chans, strides = LATENT_LEN, [2048, 1024, 512, 256, 128, 128], [8, 8, 4, 4, 2]
@@ -402,7 +403,9 @@ def run_native(args):
         l_in, l_out = l_out, l_out * st_
         elems = l_out * chans[i + 1]
         dec_bytes += 2.0 * l_in * chans[i] + 6.0 * elems        # ConvT: read s16, write raw fp32 + s16
-        dec_bytes += 3 * 4.0 * elems + (12 + 12 + 8) * elems      # 3 x (conv7: 2+2 B) + conv1: 2+4+4+2 (last: no raw write)
+        dec_bytes += (12 + 12 + 8) * elems                        # 3 x conv1 / fused unit: 2+4+4+2 B (last: no raw write)
+        if chans[i + 1] != 128:
+            dec_bytes += 3 * 4.0 * elems                          # two-launch units: conv7 writes + conv1 reads a 16-bit copy
     dec_bytes += 2.0 * l_out * 128 + 4.0 * l_out * 2             # final conv
     dec_ms_sample = decode_ms / BATCH
     gen_ms = GEN_STEPS * ms_per_step + decode_ms
