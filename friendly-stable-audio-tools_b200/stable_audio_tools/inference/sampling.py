@@ -3,10 +3,13 @@
 ``sample_k`` keeps the reference signature and behaviour (``inference/sampling.py:144-228``):
 polyexponential sigma schedule, initial noise scaled by sigma_0, variation / inpainting
 initialisation and the inpainting callback, sampler dispatch by name.  The k-diffusion 0.1.1
-pieces it relies on (``VDenoiser``, ``get_sigmas_polyexponential``, DPM-Solver++(2M/3M) SDE)
-are an un-vendored third-party dependency of the reference (``setup.py:21``) that is absent
-offline, so they are restated here from the published algorithms (Karras et al. 2022;
-Lu et al. 2022) - parity for those is unpinned by the reference.
+pieces it relies on (``VDenoiser``, ``get_sigmas_polyexponential``, DPM-Solver++(2M/3M) SDE, and
+the ``k-*`` samplers: Heun, linear multistep, DPM-2, DPM-Solver++(2S) ancestral, DPM-Solver
+fast / adaptive) are an un-vendored third-party dependency of the reference (``setup.py:21``) that
+is absent offline, so they are restated here from the published algorithms (Karras et al. 2022,
+Alg. 1/2; Lu et al. 2022, DPM-Solver and DPM-Solver++) - parity for those is unpinned by the
+reference; ``tests/test_host_logic.py`` checks every one of them against the
+closed-form probability-flow solution of a Gaussian toy problem.
 k-diffusion's Brownian-tree noise (torchsde) is replaced by one ``randn_like`` draw per
 step, which has the same distribution over the disjoint sigma intervals; pass
 ``noise_sampler=`` to inject an explicit sequence.
@@ -131,7 +134,255 @@ def sample_dpmpp_3m_sde(model, x, sigmas, extra_args=None, callback=None, disabl
     return x
 
 
-SAMPLERS = {"dpmpp-2m-sde": sample_dpmpp_2m_sde, "dpmpp-3m-sde": sample_dpmpp_3m_sde}
+def _to_d(x, sigma, denoised):
+    """Karras ODE derivative dx/dsigma = (x - D(x, sigma)) / sigma."""
+    return (x - denoised) / sigma
+
+
+@torch.no_grad()
+def sample_heun(model, x, sigmas, extra_args=None, callback=None, disable=None, **_):
+    """Karras et al. 2022, Algorithm 1 without churn: Euler step + trapezoidal correction."""
+    extra_args = extra_args or {}
+    ones = x.new_ones([x.shape[0]])
+    sig = [float(v) for v in sigmas]
+    for i in range(len(sig) - 1):
+        den = model(x, sigmas[i] * ones, **extra_args)
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": den})
+        d = _to_d(x, sig[i], den)
+        dt = sig[i + 1] - sig[i]
+        if sig[i + 1] == 0:
+            x = x + d * dt
+        else:
+            x_2 = x + d * dt
+            den_2 = model(x_2, sigmas[i + 1] * ones, **extra_args)
+            x = x + (d + _to_d(x_2, sig[i + 1], den_2)) * (0.5 * dt)
+    return x
+
+
+@torch.no_grad()
+def sample_dpm_2(model, x, sigmas, extra_args=None, callback=None, disable=None, **_):
+    """Second-order sampler with the midpoint taken in log-sigma (Karras et al. 2022, Algorithm 2 without churn)."""
+    extra_args = extra_args or {}
+    ones = x.new_ones([x.shape[0]])
+    sig = [float(v) for v in sigmas]
+    for i in range(len(sig) - 1):
+        den = model(x, sigmas[i] * ones, **extra_args)
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": den})
+        d = _to_d(x, sig[i], den)
+        if sig[i + 1] == 0:
+            x = x + d * (sig[i + 1] - sig[i])
+        else:
+            sigma_mid = math.exp(0.5 * (math.log(sig[i]) + math.log(sig[i + 1])))
+            x_2 = x + d * (sigma_mid - sig[i])
+            den_2 = model(x_2, sigma_mid * ones, **extra_args)
+            x = x + _to_d(x_2, sigma_mid, den_2) * (sig[i + 1] - sig[i])
+    return x
+
+
+def _lms_coeff(order, t, i, j):
+    """Integral over [t_i, t_{i+1}] of the j-th Lagrange basis polynomial through t_i, t_{i-1}, ..., t_{i-order+1}
+    (exact polynomial integration)."""
+    import numpy as np
+    poly = np.poly1d([1.0])
+    for k in range(order):
+        if k != j:
+            poly = poly * np.poly1d([1.0, -t[i - k]]) / (t[i - j] - t[i - k])
+    integ = poly.integ()
+    return float(integ(t[i + 1]) - integ(t[i]))
+
+
+@torch.no_grad()
+def sample_lms(model, x, sigmas, extra_args=None, callback=None, disable=None, order=4, **_):
+    """Linear multistep (Adams-Bashforth in sigma) of order <= 4 over the derivative history."""
+    extra_args = extra_args or {}
+    ones = x.new_ones([x.shape[0]])
+    sig = [float(v) for v in sigmas]
+    ds = []
+    for i in range(len(sig) - 1):
+        den = model(x, sigmas[i] * ones, **extra_args)
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": den})
+        ds.append(_to_d(x, sig[i], den))
+        if len(ds) > order:
+            ds.pop(0)
+        cur = min(i + 1, order)
+        for j, d in zip(range(cur), reversed(ds)):
+            x = x + d * _lms_coeff(cur, sig, i, j)
+    return x
+
+
+def get_ancestral_step(sigma_from, sigma_to, eta=1.0):
+    """Split a step into a deterministic part down to sigma_down and fresh noise of scale sigma_up."""
+    if not eta:
+        return sigma_to, 0.0
+    sigma_up = min(sigma_to, eta * math.sqrt(sigma_to ** 2 * (sigma_from ** 2 - sigma_to ** 2) / sigma_from ** 2))
+    return math.sqrt(sigma_to ** 2 - sigma_up ** 2), sigma_up
+
+
+@torch.no_grad()
+def sample_dpmpp_2s_ancestral(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1.0, s_noise=1.0,
+                              noise_sampler=None):
+    """DPM-Solver++(2S) with ancestral noise (Lu et al. 2022, data-prediction, single-step second order)."""
+    noise = _noise_fn(x, noise_sampler)
+    extra_args = extra_args or {}
+    ones = x.new_ones([x.shape[0]])
+    sig = [float(v) for v in sigmas]
+    for i in range(len(sig) - 1):
+        den = model(x, sigmas[i] * ones, **extra_args)
+        sigma_down, sigma_up = get_ancestral_step(sig[i], sig[i + 1], eta)
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": den})
+        if sigma_down == 0:
+            x = x + _to_d(x, sig[i], den) * (sigma_down - sig[i])
+        else:
+            t, t_next = -math.log(sig[i]), -math.log(sigma_down)
+            h = t_next - t
+            s_mid = t + 0.5 * h
+            x_2 = (math.exp(-s_mid) / math.exp(-t)) * x - math.expm1(-0.5 * h) * den
+            den_2 = model(x_2, math.exp(-s_mid) * ones, **extra_args)
+            x = (math.exp(-t_next) / math.exp(-t)) * x - math.expm1(-h) * den_2
+        if sig[i + 1] > 0 and sigma_up > 0:
+            x = x + noise(sigmas[i], sigmas[i + 1]) * (s_noise * sigma_up)
+    return x
+
+
+class _DPMSolver:
+    """DPM-Solver (Lu et al. 2022) in t = -log(sigma) with noise prediction eps = (x - D(x, sigma)) / sigma:
+    singlestep orders 1-3, the fixed-budget schedule ("fast") and the adaptive order-2/3 pair with a
+    PID step-size controller ("adaptive")."""
+
+    def __init__(self, model, extra_args=None, callback=None):
+        self.model, self.extra_args, self.callback = model, extra_args or {}, callback
+        self.nfe = 0
+
+    @staticmethod
+    def sigma(t):
+        return math.exp(-t)
+
+    def eps(self, cache, key, x, t):
+        if key in cache:
+            return cache[key], cache
+        sig = self.sigma(t)
+        eps = (x - self.model(x, x.new_ones([x.shape[0]]) * sig, **self.extra_args)) / sig
+        self.nfe += 1
+        return eps, {key: eps, **cache}
+
+    def step1(self, x, t, t_next, cache=None):
+        cache = cache or {}
+        h = t_next - t
+        eps, cache = self.eps(cache, "eps", x, t)
+        return x - self.sigma(t_next) * math.expm1(h) * eps, cache
+
+    def step2(self, x, t, t_next, r1=0.5, cache=None):
+        cache = cache or {}
+        h = t_next - t
+        eps, cache = self.eps(cache, "eps", x, t)
+        s1 = t + r1 * h
+        u1 = x - self.sigma(s1) * math.expm1(r1 * h) * eps
+        eps_r1, cache = self.eps(cache, "eps_r1", u1, s1)
+        x_2 = x - self.sigma(t_next) * math.expm1(h) * eps - self.sigma(t_next) / (2 * r1) * math.expm1(h) * (eps_r1 - eps)
+        return x_2, cache
+
+    def step3(self, x, t, t_next, r1=1 / 3, r2=2 / 3, cache=None):
+        cache = cache or {}
+        h = t_next - t
+        eps, cache = self.eps(cache, "eps", x, t)
+        s1, s2 = t + r1 * h, t + r2 * h
+        u1 = x - self.sigma(s1) * math.expm1(r1 * h) * eps
+        eps_r1, cache = self.eps(cache, "eps_r1", u1, s1)
+        u2 = (x - self.sigma(s2) * math.expm1(r2 * h) * eps
+              - self.sigma(s2) * (r2 / r1) * (math.expm1(r2 * h) / (r2 * h) - 1) * (eps_r1 - eps))
+        eps_r2, cache = self.eps(cache, "eps_r2", u2, s2)
+        x_3 = (x - self.sigma(t_next) * math.expm1(h) * eps
+               - self.sigma(t_next) / r2 * (math.expm1(h) / h - 1) * (eps_r2 - eps))
+        return x_3, cache
+
+    def _report(self, x, i, t, cache):
+        if self.callback is not None and "eps" in cache:
+            sig = self.sigma(t)
+            self.callback({"x": x, "i": i, "t": t, "sigma": x.new_tensor(sig), "sigma_hat": x.new_tensor(sig),
+                           "denoised": x - sig * cache["eps"]})
+
+    def fast(self, x, t_start, t_end, nfe):
+        if nfe < 1:
+            raise ValueError("nfe must be at least 1")
+        m = nfe // 3 + 1
+        ts = [t_start + (t_end - t_start) * k / m for k in range(m + 1)]
+        orders = [3] * (m - 2) + [2, 1] if nfe % 3 == 0 else [3] * (m - 1) + [nfe % 3]
+        for i, order in enumerate(orders):
+            t, t_next = ts[i], ts[i + 1]
+            eps, cache = self.eps({}, "eps", x, t)
+            self._report(x, i, t, cache)
+            if order == 1:
+                x, _ = self.step1(x, t, t_next, cache=cache)
+            elif order == 2:
+                x, _ = self.step2(x, t, t_next, cache=cache)
+            else:
+                x, _ = self.step3(x, t, t_next, cache=cache)
+        return x
+
+    def adaptive(self, x, t_start, t_end, order=3, rtol=0.05, atol=0.0078, h_init=0.05, pcoeff=0.0, icoeff=1.0,
+                 dcoeff=0.0, accept_safety=0.81):
+        if order not in (2, 3):
+            raise ValueError("order should be 2 or 3")
+        forward = t_end > t_start
+        h = abs(h_init) * (1 if forward else -1)
+        b1, b2, b3 = (pcoeff + icoeff + dcoeff) / order, -(pcoeff + 2 * dcoeff) / order, dcoeff / order
+        errs = None
+        s, x_prev, i = t_start, x, 0
+        while (s < t_end - 1e-5) if forward else (s > t_end + 1e-5):
+            t = min(t_end, s + h) if forward else max(t_end, s + h)
+            eps, cache = self.eps({}, "eps", x, s)
+            if order == 2:
+                x_low, cache = self.step1(x, s, t, cache=cache)
+                x_high, cache = self.step2(x, s, t, cache=cache)
+            else:
+                x_low, cache = self.step2(x, s, t, r1=1 / 3, cache=cache)
+                x_high, cache = self.step3(x, s, t, cache=cache)
+            delta = torch.maximum(torch.full_like(x_low, atol), rtol * torch.maximum(x_low.abs(), x_prev.abs()))
+            error = float(torch.linalg.norm((x_low - x_high) / delta) / x.numel() ** 0.5)
+            inv = 1.0 / (error + 1e-8)
+            if errs is None:
+                errs = [inv, inv, inv]
+            errs[0] = inv
+            factor = errs[0] ** b1 * errs[1] ** b2 * errs[2] ** b3
+            factor = 1 + math.atan(factor - 1)
+            accept = factor >= accept_safety
+            if accept:
+                errs[2], errs[1] = errs[1], errs[0]
+                x_prev, x, s = x_low, x_high, t
+                self._report(x, i, s, cache)
+                i += 1
+            h *= factor
+        return x
+
+
+@torch.no_grad()
+def sample_dpm_fast(model, x, sigma_min, sigma_max, n, extra_args=None, callback=None, disable=None, **_):
+    """DPM-Solver with a fixed budget of n model evaluations between sigma_max and sigma_min."""
+    if sigma_min <= 0 or sigma_max <= 0:
+        raise ValueError("sigma_min and sigma_max must not be 0")
+    return _DPMSolver(model, extra_args, callback).fast(x, -math.log(sigma_max), -math.log(sigma_min), n)
+
+
+@torch.no_grad()
+def sample_dpm_adaptive(model, x, sigma_min, sigma_max, extra_args=None, callback=None, disable=None, order=3,
+                        rtol=0.05, atol=0.0078, h_init=0.05, pcoeff=0.0, icoeff=1.0, dcoeff=0.0, accept_safety=0.81, **_):
+    """DPM-Solver-12/23 with adaptive step size (PID controller on the embedded error estimate)."""
+    if sigma_min <= 0 or sigma_max <= 0:
+        raise ValueError("sigma_min and sigma_max must not be 0")
+    return _DPMSolver(model, extra_args, callback).adaptive(x, -math.log(sigma_max), -math.log(sigma_min), order, rtol,
+                                                            atol, h_init, pcoeff, icoeff, dcoeff, accept_safety)
+
+
+# sampler_type -> (function, takes a sigma schedule?)  (reference inference/sampling.py:211-228)
+SAMPLERS = {
+    "k-heun": sample_heun, "k-lms": sample_lms, "k-dpmpp-2s-ancestral": sample_dpmpp_2s_ancestral, "k-dpm-2": sample_dpm_2,
+    "k-dpm-fast": sample_dpm_fast, "k-dpm-adaptive": sample_dpm_adaptive,
+    "dpmpp-2m-sde": sample_dpmpp_2m_sde, "dpmpp-3m-sde": sample_dpmpp_3m_sde,
+}
 
 
 def get_bmask(i, steps, mask):
@@ -169,5 +420,11 @@ def sample_k(model_fn, noise, init_data=None, mask=None, steps=100, sampler_type
                 return inpainting_callback(args), callback(args)
     else:
         x = noise
+    if sampler_type == "k-dpm-fast":
+        return sample_dpm_fast(denoiser, x, sigma_min, sigma_max, steps, disable=disable_tqdm, callback=wrapped_callback,
+                               extra_args=extra_args)
+    if sampler_type == "k-dpm-adaptive":
+        return sample_dpm_adaptive(denoiser, x, sigma_min, sigma_max, rtol=0.01, atol=0.01, disable=disable_tqdm,
+                                   callback=wrapped_callback, extra_args=extra_args)
     return SAMPLERS[sampler_type](denoiser, x, sigmas, disable=disable_tqdm, callback=wrapped_callback,
                                   extra_args=extra_args, noise_sampler=noise_sampler)

@@ -189,3 +189,35 @@ sys.stdout.flush()
                        capture_output=True, text=True, timeout=240, env=env)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "rank 0 ok" in p.stdout and "rank 1 ok" in p.stdout
+
+
+def test_every_sampler_type_solves_the_gaussian_toy_problem():
+    """All sampler_type values of the reference's sample_k (inference/sampling.py:211-228) exist and solve a
+    problem with a closed-form answer: data ~ N(0, s^2), optimal denoiser D(x, sigma) = x s^2 / (s^2 + sigma^2);
+    the probability-flow ODE gives x(sigma) = x(sigma_max) sqrt((s^2 + sigma^2) / (s^2 + sigma_max^2)), and the
+    stochastic samplers must end with standard deviation s."""
+    import math
+    from stable_audio_tools.inference import sampling as S
+    s0, smin, smax = 0.7, 0.03, 80.0
+
+    def model_fn(xin, t, **kw):      # the v-objective network whose VDenoiser wrapping equals D
+        sigma = torch.tan(t * math.pi / 2).view(-1, *([1] * (xin.ndim - 1)))
+        x = xin * (sigma ** 2 + 1).sqrt()
+        den = x * s0 ** 2 / (s0 ** 2 + sigma ** 2)
+        return (den - x / (sigma ** 2 + 1)) / (-sigma / (sigma ** 2 + 1).sqrt())
+
+    assert set(S.SAMPLERS) == {"k-heun", "k-lms", "k-dpmpp-2s-ancestral", "k-dpm-2", "k-dpm-fast", "k-dpm-adaptive",
+                               "dpmpp-2m-sde", "dpmpp-3m-sde"}
+    torch.manual_seed(0)
+    noise = torch.randn(4, 8, 2048, dtype=torch.float64)
+    tol = {"k-heun": 5e-3, "k-lms": 2e-3, "k-dpm-2": 1e-3, "k-dpm-fast": 5e-4, "k-dpm-adaptive": 5e-2}
+    for name in S.SAMPLERS:
+        torch.manual_seed(1)
+        out = S.sample_k(model_fn, noise, steps=60, sampler_type=name, sigma_min=smin, sigma_max=smax, device="cpu")
+        assert out.shape == noise.shape and torch.isfinite(out).all()
+        if name in tol:
+            end = smin if name in ("k-dpm-fast", "k-dpm-adaptive") else 0.0    # those two stop at sigma_min
+            ref = noise * smax * math.sqrt(s0 ** 2 + end ** 2) / math.sqrt(s0 ** 2 + smax ** 2)
+            assert float((out - ref).norm() / ref.norm()) < tol[name], name
+        else:
+            assert abs(float(out.std()) - s0) < 0.02, name
