@@ -444,7 +444,11 @@ def run_native(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<EpiSwiglu> (FF-in 8200x12288x1536)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": (achieved / peak_tf) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "frac": (achieved / peak_tf) if achieved else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel from the
+                     # `ncu --set full` capture summarised in profiles/r01_ncu_ff_in_gemm.txt (63.2 + 62.6 MB;
+                     # algorithmic A + W + out = 163.7 MB, part of the 16-bit output stays in the 126 MB L2)
+                     "traffic": 125806592, "traffic_unit": "bytes per launch (ncu)", "peak_source": peak_src,
                      "avg_launch_ms": ff_in_ms},
         "step_tflops": step_tflops, "step_frac_of_peak": step_tflops / peak_tf,
         "profiled_pass_ms_per_step": profiled_ms_per_step,
