@@ -663,6 +663,39 @@ __device__ __forceinline__ float snake_fast(float v, float a, float ib) {
   return fmaf(ib, sn * sn, v);
 }
 
+// Packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2: one issue slot for two lanes' worth of
+// work) for the convolution epilogues, which are issue-bound rather than FMA-throughput-bound.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// snake_fast on two values at once: same operations and roundings as the scalar version.
+__device__ __forceinline__ uint64_t snake_fast2(uint64_t v, uint64_t a, uint64_t ib) {
+  float t0, t1;
+  f2_unpack(f2_mul(v, a), t0, t1);
+  const uint64_t sn = f2_pack(__sinf(t0), __sinf(t1));
+  return f2_fma(ib, f2_mul(sn, sn), v);
+}
+
 // Epilogue of every tensor-core convolution of the Oobleck VAE (models/autoencoders.py:45-116):
 //   y = acc + bias[co] (+ resid[pos, co])            ResidualUnit skip :66-68
 //   raw_out[pos, co] = y (fp32, optional)            kept only where a later skip needs it
@@ -734,29 +767,32 @@ struct EpiConv {
     __syncwarp();
     const Seg sg = seg_of(p, c);
     const int co = sg.co;
-    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), a4 = b4, ib4 = b4;
-    if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+    ulonglong2 b2 = make_ulonglong2(0ull, 0ull), a2 = b2, ib2 = b2;   // (x,y) and (z,w) pairs; 0 bits = 0.f
+    if (p.bias) b2 = __ldg(reinterpret_cast<const ulonglong2*>(p.bias + co));
     const bool snake = p.s16_out != nullptr && p.sn_a != nullptr;
     if (snake) {
-      a4 = __ldg(reinterpret_cast<const float4*>(p.sn_a + co));
-      ib4 = __ldg(reinterpret_cast<const float4*>(p.sn_ib + co));
+      a2 = __ldg(reinterpret_cast<const ulonglong2*>(p.sn_a + co));
+      ib2 = __ldg(reinterpret_cast<const ulonglong2*>(p.sn_ib + co));
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       size_t idx;
       if (seg_index(p, c, sg, i, &idx)) {
-        float4 v = *reinterpret_cast<const float4*>(st + (r0 + 4 * i) * 36 + 4 * g);
-        v.x += b4.x + rs[i].x; v.y += b4.y + rs[i].y; v.z += b4.z + rs[i].z; v.w += b4.w + rs[i].w;
-        if (p.raw_out) *reinterpret_cast<float4*>(p.raw_out + idx) = v;
+        const ulonglong2 acc = *reinterpret_cast<const ulonglong2*>(st + (r0 + 4 * i) * 36 + 4 * g);
+        const uint64_t r01 = f2_pack(rs[i].x, rs[i].y), r23 = f2_pack(rs[i].z, rs[i].w);
+        uint64_t v01 = f2_add(acc.x, f2_add(b2.x, r01));
+        uint64_t v23 = f2_add(acc.y, f2_add(b2.y, r23));
+        if (p.raw_out) *reinterpret_cast<ulonglong2*>(p.raw_out + idx) = make_ulonglong2(v01, v23);
         if (p.s16_out) {
           if (snake) {
-            v.x = snake_fast(v.x, a4.x, ib4.x);
-            v.y = snake_fast(v.y, a4.y, ib4.y);
-            v.z = snake_fast(v.z, a4.z, ib4.z);
-            v.w = snake_fast(v.w, a4.w, ib4.w);
+            v01 = snake_fast2(v01, a2.x, ib2.x);
+            v23 = snake_fast2(v23, a2.y, ib2.y);
           }
+          float x0, x1, x2, x3;
+          f2_unpack(v01, x0, x1);
+          f2_unpack(v23, x2, x3);
           *reinterpret_cast<uint2*>(static_cast<uint16_t*>(p.s16_out) + idx) =
-              make_uint2(Op16<BF16>::pack(v.x, v.y), Op16<BF16>::pack(v.z, v.w));
+              make_uint2(Op16<BF16>::pack(x0, x1), Op16<BF16>::pack(x2, x3));
         }
       }
     }

@@ -266,13 +266,14 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         const float* pb = prm + ci * 32;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 b4 = *reinterpret_cast<const float4*>(pb + 4 * j);
-          const float4 a4 = *reinterpret_cast<const float4*>(pb + Cfg::kC + 4 * j);
-          const float4 i4 = *reinterpret_cast<const float4*>(pb + 2 * Cfg::kC + 4 * j);
-          const float v0 = snake_fast(__uint_as_float(r[4 * j]) + b4.x, a4.x, i4.x);
-          const float v1 = snake_fast(__uint_as_float(r[4 * j + 1]) + b4.y, a4.y, i4.y);
-          const float v2 = snake_fast(__uint_as_float(r[4 * j + 2]) + b4.z, a4.z, i4.z);
-          const float v3 = snake_fast(__uint_as_float(r[4 * j + 3]) + b4.w, a4.w, i4.w);
+          const ulonglong2 b2 = *reinterpret_cast<const ulonglong2*>(pb + 4 * j);
+          const ulonglong2 a2 = *reinterpret_cast<const ulonglong2*>(pb + Cfg::kC + 4 * j);
+          const ulonglong2 i2 = *reinterpret_cast<const ulonglong2*>(pb + 2 * Cfg::kC + 4 * j);
+          const uint64_t acc01 = (static_cast<uint64_t>(r[4 * j + 1]) << 32) | r[4 * j];
+          const uint64_t acc23 = (static_cast<uint64_t>(r[4 * j + 3]) << 32) | r[4 * j + 2];
+          float v0, v1, v2, v3;
+          f2_unpack(snake_fast2(f2_add(acc01, b2.x), a2.x, i2.x), v0, v1);
+          f2_unpack(snake_fast2(f2_add(acc23, b2.y), a2.y, i2.y), v2, v3);
           o[2 * j] = Op16<BF16>::pack(v0, v1);
           o[2 * j + 1] = Op16<BF16>::pack(v2, v3);
         }

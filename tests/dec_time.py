@@ -27,5 +27,27 @@ for _ in range(reps):
     y = dec(z)
 e1.record()
 torch.cuda.synchronize()
+# box-speed reference (boxes of the pool differ by several %): a cuBLAS bf16 GEMM and a device copy
+a = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+b = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+for _ in range(3):
+    c = a @ b
+r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+r0.record()
+for _ in range(20):
+    c = a @ b
+r1.record()
+torch.cuda.synchronize()
+gemm_tf = 20 * 2 * 8192 ** 3 / (r0.elapsed_time(r1) / 1e3) / 1e12
+src = torch.empty(1 << 30, device="cuda", dtype=torch.uint8)
+dst = torch.empty_like(src)
+dst.copy_(src)
+r0.record()
+for _ in range(10):
+    dst.copy_(src)
+r1.record()
+torch.cuda.synchronize()
+copy_gbs = 10 * 2 * (1 << 30) / (r0.elapsed_time(r1) / 1e3) / 1e9
+print("box: cublas bf16 %.0f TF/s, copy %.0f GB/s" % (gemm_tf, copy_gbs))
 tag = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("SATB_"))
 print("decode_ms %.3f  [%s]" % (e0.elapsed_time(e1) / reps, tag), flush=True)
