@@ -49,9 +49,6 @@ int satb_attention(const void* q16, const void* k16, const void* v16, void* o16,
                    int bf16, void* stream) {
   SATB_REQUIRE(q16 && k16 && v16 && o16, "null argument");
   const int64_t dq = static_cast<int64_t>(H) * 64, dk = static_cast<int64_t>(Hkv) * 64;
-  if (attention_use_legacy())
-    return launch_attention(q16, k16, v16, o16, dq, dk, dk, dq, Nq * dq, Nk * dk, Nk * dk, Nq * dq, B, H, Hkv, Nq, Nk, 64,
-                            bf16 != 0, static_cast<cudaStream_t>(stream));
   return launch_attention_tc(q16, k16, v16, o16, dq, dk, dk, dq, Nq * dq, Nk * dk, Nk * dk, Nq * dq, static_cast<int>(dq),
                              static_cast<int>(dk), static_cast<int>(dk), 0, 0, 0, B, H, Hkv, Nq, Nk, bf16 != 0,
                              static_cast<cudaStream_t>(stream));

@@ -561,13 +561,9 @@ static int dit_forward_impl(SatbDit* d, const float* x, const float* t, float* o
     {
       ProfScope ps(d, PROF_ATTN_SELF, st);
       const int64_t qs = static_cast<int64_t>(N_seq) * 3 * D;
-      if (attention_use_legacy())
-        SATB_PROPAGATE(launch_attention(qkv, qkv + D, qkv + 2 * D, att, 3 * D, 3 * D, 3 * D, D, qs, qs, qs,
-                                        static_cast<int64_t>(N_seq) * D, R, H, H, N_seq, N_seq, d->dh, BF16, st));
-      else
-        SATB_PROPAGATE(launch_attention_tc(qkv, qkv, qkv, att, 3 * D, 3 * D, 3 * D, D, qs, qs, qs,
-                                           static_cast<int64_t>(N_seq) * D, 3 * D, 3 * D, 3 * D, 0, D, 2 * D, R, H, H,
-                                           N_seq, N_seq, BF16, st));
+      SATB_PROPAGATE(launch_attention_tc(qkv, qkv, qkv, att, 3 * D, 3 * D, 3 * D, D, qs, qs, qs,
+                                         static_cast<int64_t>(N_seq) * D, 3 * D, 3 * D, 3 * D, 0, D, 2 * D, R, H, H,
+                                         N_seq, N_seq, BF16, st));
     }
     {
       ProfScope ps(d, PROF_ATTN_OUT, st);
@@ -586,14 +582,9 @@ static int dit_forward_impl(SatbDit* d, const float* x, const float* t, float* o
       }
       const uint16_t* kv = d->ws_kv.as<uint16_t>() + static_cast<size_t>(i) * d->Rc * d->Mctx * 2 * d->ce;
       const int64_t kvs = static_cast<int64_t>(d->Mctx) * 2 * d->ce;
-      if (attention_use_legacy())
-        SATB_PROPAGATE(launch_attention(q16, kv, kv + d->ce, att, D, 2 * d->ce, 2 * d->ce, D,
-                                        static_cast<int64_t>(N_seq) * D, kvs, kvs, static_cast<int64_t>(N_seq) * D, d->Rc,
-                                        H, Hkv, N_seq, d->Mctx, d->dh, BF16, st));
-      else
-        SATB_PROPAGATE(launch_attention_tc(q16, kv, kv, att, D, 2 * d->ce, 2 * d->ce, D, static_cast<int64_t>(N_seq) * D,
-                                           kvs, kvs, static_cast<int64_t>(N_seq) * D, D, 2 * d->ce, 2 * d->ce, 0, 0,
-                                           d->ce, d->Rc, H, Hkv, N_seq, d->Mctx, BF16, st));
+      SATB_PROPAGATE(launch_attention_tc(q16, kv, kv, att, D, 2 * d->ce, 2 * d->ce, D, static_cast<int64_t>(N_seq) * D,
+                                         kvs, kvs, static_cast<int64_t>(N_seq) * D, D, 2 * d->ce, 2 * d->ce, 0, 0,
+                                         d->ce, d->Rc, H, Hkv, N_seq, d->Mctx, BF16, st));
       {
         EpiResidual::Params ep{h, D, nullptr, nullptr, N_seq, 0, 1};
         SATB_PROPAGATE((linear_auto<EpiResidual, BF16>(d->tmaps, att, D, Mc, D, W.w_co, D, ep, st)));

@@ -5,20 +5,15 @@
 
 namespace satb {
 
-// ---- attention.cu
-int launch_attention(const void* q, const void* k, const void* v, void* o, int64_t ldq, int64_t ldk, int64_t ldv,
-                     int64_t ldo, int64_t q_bs, int64_t k_bs, int64_t v_bs, int64_t o_bs, int batch, int H, int H_kv,
-                     int Nq, int Nk, int head_dim, bool bf16, cudaStream_t stream);
-
 // ---- attention_tc.cu (tcgen05)
 int launch_attention_tc(const void* q, const void* k, const void* v, void* o, int64_t ldq, int64_t ldk, int64_t ldv,
                         int64_t ldo, int64_t q_bs, int64_t k_bs, int64_t v_bs, int64_t o_bs, int q_cols, int k_cols,
                         int v_cols, int q_col, int k_col, int v_col, int batch, int H, int H_kv, int Nq, int Nk,
                         bool bf16, cudaStream_t stream, unsigned long long* dbg = nullptr);
-bool attention_use_legacy();
+// debugging switches (environment variables; the defaults are the production path)
 bool conv_halo_enabled();     // SATB_CONV_HALO=off: generic 7-tap loads for the final conv (A/B debugging)
 bool resunit_use_fused();      // SATB_RESUNIT=unfused runs the 128-channel ResidualUnits as two GEMM launches (A/B debugging)
-bool gemm_use_2cta();          // SATB_GEMM=1cta disables the CTA-pair GEMM (A/B debugging)   // SATB_ATTN=mma selects the round-1 mma.sync kernel (debug only)
+bool gemm_use_2cta();          // SATB_GEMM=1cta disables the CTA-pair GEMM (A/B debugging)
 
 // ---- elementwise.cu
 // LayerNorm over the last dim (eps 1e-5), optional adaLN modulation y*(1+scale)+shift, 16-bit output.

@@ -16,15 +16,6 @@ unsigned long long g_launch_count = 0;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 const char* get_last_error() { return g_last_error.c_str(); }
 
-bool attention_use_legacy() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SATB_ATTN");
-    v = (e && std::string(e) == "mma") ? 1 : 0;
-  }
-  return v == 1;
-}
-
 bool gemm_use_2cta() {
   static int v = -1;
   if (v < 0) {

@@ -78,7 +78,7 @@ def test_sample_k_initialisation_modes():
     assert len(calls) == 3 and calls[0]["cfg_scale"] == 3.0
     assert torch.isfinite(out).all()
     with pytest.raises(NotImplementedError):
-        sample_k(toy, noise, steps=3, sampler_type="k-heun", device="cpu")
+        sample_k(toy, noise, steps=3, sampler_type="no-such-sampler", device="cpu")
 
 
 def test_get_conditioning_inputs_routing():
