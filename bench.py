@@ -442,7 +442,7 @@ def run_native(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<EpiSwiglu> (FF-in 8200x12288x1536)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_2cta_kernel<EpiSwiglu, 256> (FF-in 8200x12288x1536)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (achieved / peak_tf) if achieved else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel from the
