@@ -392,6 +392,26 @@ def run_native(args):
         tmax = torch.tensor([decode_ms], device=device)
         td.all_reduce(tmax, op=td.ReduceOp.MAX)
         decode_ms = float(tmax.item())
+    # ---------------- other BASELINE.json shapes, for the record (single GPU only) ---------------
+    # configs[1]: one prompt (2 CFG rows x 1025 tokens); configs[4]: SA-2.0 length (L = 6144 latents, 1 prompt).
+    extra_shapes = {}
+    if world == 1:
+        for name, L_x in (("single_prompt_L1024", LATENT_LEN), ("single_prompt_L6144_sa2_length", 6144)):
+            xs = torch.randn(1, 64, L_x, device=device)
+            ts = torch.full((1,), 0.5, device=device)
+            kw = dict(cross_attn_cond=cross[:1].contiguous(), cross_attn_mask=mask[:1].contiguous(),
+                      global_cond=glob[:1].contiguous(), cfg_scale=CFG_SCALE, batch_cfg=True, rescale_cfg=True)
+            for _ in range(3):
+                wrapper(xs, ts, **kw)
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(10):
+                wrapper(xs, ts, **kw)
+            s1.record()
+            torch.cuda.synchronize()
+            extra_shapes[name] = {"ms_per_model_call": s0.elapsed_time(s1) / 10, "rows": 2, "tokens": L_x + 1}
+
     # Oobleck decoder roofline bookkeeping, per sample of L = 1024 latents:
     #   FLOPs 5.163e12; bytes for the fusion level implemented (16-bit activated copy in/out of every
     #   tensor-core conv, fp32 raw skip stream read+written once per ResidualUnit, the 128-channel
@@ -454,6 +474,7 @@ def run_native(args):
         "profiled_pass_ms_per_step": profiled_ms_per_step,
         "kernel_breakdown": breakdown,
         "decode_ms_batch": decode_ms, "audio_sec_per_s_100step": audio_sec_per_s,
+        "other_shapes": extra_shapes,
         "oobleck_decoder": {"ms_per_sample": dec_ms_sample, "tflops": dec_flops / (dec_ms_sample / 1e3) / 1e12,
                             "frac_of_tensor_peak": dec_flops / (dec_ms_sample / 1e3) / 1e12 / peak_tf,
                             "algorithmic_gb_per_sample": dec_bytes / 1e9,
