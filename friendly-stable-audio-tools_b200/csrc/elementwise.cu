@@ -180,34 +180,67 @@ __global__ void fourier_kernel(const float* __restrict__ t, const float* __restr
 // one warp per output column, fp32 weights and accumulation, up to 8 rows per pass.
 __device__ __forceinline__ float silu_acc(float x) { return x / (1.0f + expf(-x)); }
 
+// The (at most 8) input rows of a pass are staged in shared memory once per block; every lane then has all
+// its weight loads (K / 128 float4, <= 16) in flight at once instead of a 4-deep loop, which is what made
+// the 1536 x 1536 timestep-embedding layer latency-bound (96 us under ncu for 9.4 MB of weights).
+constexpr int kSkinnyMaxVec = 16;   // K <= 16 * 128 = 2048 per fast pass; larger K falls back to the loop
+
 __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restrict__ in, const float* __restrict__ W,
                                                             const float* __restrict__ bias,
                                                             const float* __restrict__ add, float* __restrict__ out,
                                                             int R, int K, int N, int silu_out) {
+  extern __shared__ float4 xs4[];   // [8][K / 4]
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (n >= N) return;
-  const float4* wr = reinterpret_cast<const float4*>(W + static_cast<size_t>(n) * K);
   const int k4n = K >> 2;
+  const bool col_ok = n < N;
+  const float4* wr = reinterpret_cast<const float4*>(W + static_cast<size_t>(col_ok ? n : 0) * K);
+  float4 w[kSkinnyMaxVec];
+  const bool fast = k4n <= kSkinnyMaxVec * 32;
+  if (fast) {
+#pragma unroll
+    for (int i = 0; i < kSkinnyMaxVec; ++i)
+      w[i] = (col_ok && lane + 32 * i < k4n) ? __ldg(wr + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int r0 = 0; r0 < R; r0 += 8) {
+    const int rows = R - r0 < 8 ? R - r0 : 8;
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * k4n; i += blockDim.x)
+      xs4[i] = __ldg(reinterpret_cast<const float4*>(in + static_cast<size_t>(r0) * K) + i);
+    __syncthreads();
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll 4
-    for (int k4 = lane; k4 < k4n; k4 += 32) {
-      const float4 w = __ldg(wr + k4);
+    if (fast) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (r0 + j < R) {
-          const float4 x = __ldg(reinterpret_cast<const float4*>(in + static_cast<size_t>(r0 + j) * K) + k4);
-          acc[j] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[j]))));
+      for (int i = 0; i < kSkinnyMaxVec; ++i) {
+        const int k4 = lane + 32 * i;
+        if (k4 < k4n) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < rows) {
+              const float4 x = xs4[j * k4n + k4];
+              acc[j] = fmaf(x.x, w[i].x, fmaf(x.y, w[i].y, fmaf(x.z, w[i].z, fmaf(x.w, w[i].w, acc[j]))));
+            }
+          }
+        }
+      }
+    } else {
+      for (int k4 = lane; k4 < k4n; k4 += 32) {
+        const float4 wv = col_ok ? __ldg(wr + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < rows) {
+            const float4 x = xs4[j * k4n + k4];
+            acc[j] = fmaf(x.x, wv.x, fmaf(x.y, wv.y, fmaf(x.z, wv.z, fmaf(x.w, wv.w, acc[j]))));
+          }
         }
       }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float s = warp_sum(acc[j]);
-      if (lane == 0 && r0 + j < R) {
+      if (lane == 0 && col_ok && j < rows) {
         float v = s + (bias ? bias[n] : 0.f);
         if (add) v += add[static_cast<size_t>(r0 + j) * N + n];
         if (silu_out) v = silu_acc(v);
@@ -353,7 +386,14 @@ int launch_skinny_linear(const float* in, const float* W, const float* bias, con
                          int K, int N, int silu_out, cudaStream_t stream) {
   SATB_REQUIRE(R >= 1 && R <= 4096, "skinny linear: bad row count");
   SATB_REQUIRE(K % 4 == 0, "skinny linear: K must be a multiple of 4");
-  skinny_linear_kernel<<<ceil_div(N, 8), 256, 0, stream>>>(in, W, bias, add, out, R, K, N, silu_out);
+  const size_t smem = static_cast<size_t>(8) * K * sizeof(float);
+  SATB_REQUIRE(smem <= 200 * 1024, "skinny linear: K too large for the shared-memory row stage");
+  static size_t attr_smem = 48 * 1024;
+  if (smem > attr_smem) {
+    SATB_CHECK_CUDA(cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_smem = smem;
+  }
+  skinny_linear_kernel<<<ceil_div(N, 8), 256, smem, stream>>>(in, W, bias, add, out, R, K, N, silu_out);
   count_launch();
   SATB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -7,7 +7,7 @@ import typing as tp
 import numpy as np
 import torch
 
-from .sampling import sample_k
+from .sampling import sample_k, sample_rf
 from .utils import prepare_audio
 
 
@@ -87,11 +87,18 @@ def generate_diffusion_cond(model, steps: int = 250, cfg_scale: float = 6,
     noise = noise.type(model_dtype)
     conditioning_inputs = {k: (v.type(model_dtype) if v is not None else v) for k, v in conditioning_inputs.items()}
 
-    if model.diffusion_objective != "v":
-        raise NotImplementedError("only the v-objective (k-diffusion) path is on the native hot path")
-    sampled = sample_k(model.model, noise, init_audio, mask, steps, **sampler_kwargs, **conditioning_inputs,
-                       **negative_inputs, cfg_scale=cfg_scale, batch_cfg=True, rescale_cfg=True, device=device,
-                       disable_tqdm=disable_tqdm)
+    if model.diffusion_objective == "v":
+        sampled = sample_k(model.model, noise, init_audio, mask, steps, **sampler_kwargs, **conditioning_inputs,
+                           **negative_inputs, cfg_scale=cfg_scale, batch_cfg=True, rescale_cfg=True, device=device,
+                           disable_tqdm=disable_tqdm)
+    elif model.diffusion_objective == "rectified_flow":
+        # discrete Euler on the velocity prediction (reference generation.py:236-246); no sigma_min / sampler choice
+        rf_kwargs = {k: v for k, v in sampler_kwargs.items() if k not in ("sigma_min", "sampler_type")}
+        sampled = sample_rf(model.model, noise, init_data=init_audio, steps=steps, **rf_kwargs, **conditioning_inputs,
+                            **negative_inputs, cfg_scale=cfg_scale, batch_cfg=True, rescale_cfg=True, device=device,
+                            disable_tqdm=disable_tqdm)
+    else:
+        raise NotImplementedError(f"diffusion objective '{model.diffusion_objective}'")
     del noise, conditioning_tensors, conditioning_inputs
 
     if model.pretransform and not return_latents:

@@ -428,3 +428,29 @@ def sample_k(model_fn, noise, init_data=None, mask=None, steps=100, sampler_type
                                    callback=wrapped_callback, extra_args=extra_args)
     return SAMPLERS[sampler_type](denoiser, x, sigmas, disable=disable_tqdm, callback=wrapped_callback,
                                   extra_args=extra_args, noise_sampler=noise_sampler)
+
+
+@torch.no_grad()
+def sample_discrete_euler(model, x, steps, sigma_max=1, callback=None, **extra_args):
+    """Rectified-flow sampling (reference inference/sampling.py:29-60): the network predicts the velocity and
+    the state is integrated from t = sigma_max down to 0 on a uniform grid, x += (t_next - t) * v(x, t)."""
+    ts = torch.linspace(sigma_max, 0, steps + 1)
+    ones = x.new_ones([x.shape[0]])
+    for i in range(steps):
+        t_curr, t_next = float(ts[i]), float(ts[i + 1])
+        v = model(x, t_curr * ones, **extra_args)
+        if callback is not None:
+            callback({"x": x, "i": i, "t": t_curr, "denoised": x - t_curr * v})
+        x = x + (t_next - t_curr) * v
+    return x
+
+
+def sample_rf(model_fn, noise, init_data=None, steps=100, sigma_max=1, device="cuda", callback=None, cond_fn=None,
+              disable_tqdm: bool = False, **extra_args):
+    """Reference inference/sampling.py:236-270: plain noise, or a variation that starts from the
+    (1 - sigma_max, sigma_max) interpolation of init_data and noise."""
+    if cond_fn is not None:
+        raise NotImplementedError("guidance through cond_fn needs autograd through the model (inference-only here)")
+    sigma_max = min(sigma_max, 1)
+    x = noise if init_data is None else init_data * (1 - sigma_max) + noise * sigma_max
+    return sample_discrete_euler(model_fn, x, steps, sigma_max, callback=callback, **extra_args)
