@@ -46,8 +46,10 @@ class DiffusionTransformer(nn.Module):
         if transformer_type != "continuous_transformer":
             raise NotImplementedError("only transformer_type='continuous_transformer' is on the native hot path "
                                       "(the reference's x-transformers branch needs an un-vendored dependency)")
-        if patch_size != 1 or input_concat_dim != 0 or prepend_cond_dim != 0:
-            raise NotImplementedError("patch_size>1 / input_concat / prepend_cond are not on the native hot path yet")
+        if input_concat_dim != 0 or prepend_cond_dim != 0:
+            raise NotImplementedError("input_concat / prepend_cond are not on the native hot path yet")
+        if patch_size < 1:
+            raise ValueError("patch_size must be >= 1")
         if global_cond_type not in ("prepend", "adaLN"):
             raise ValueError(f"unknown global_cond_type {global_cond_type}")
         self.patch_size = patch_size
@@ -116,11 +118,15 @@ class DiffusionTransformer(nn.Module):
     def _handle(self, device):
         lib = _native.lib()
         if self.__dict__["_h"] is None:
+            # patch_size p > 1 (dit.py:206-207,221-222): tokens are groups of p positions with features (c p).
+            # The native model simply sees io_channels * p channels and L / p positions; forward() does the
+            # two rearranges, and the 1x1 pre/post convs (which act per position on the un-patched signal)
+            # are handed over as kron(W, I_p) so that the native fold into project_in/out stays generic.
             cfg = _native.SatbDitConfig(
-                io_channels=self.io_channels, embed_dim=self.embed_dim, depth=self.depth, num_heads=self.num_heads,
+                io_channels=self.io_channels * self.patch_size, embed_dim=self.embed_dim, depth=self.depth, num_heads=self.num_heads,
                 cond_token_dim=self.cond_token_dim, global_cond_dim=self.global_cond_dim,
                 project_cond_tokens=int(self.project_cond_tokens), project_global_cond=int(self.project_global_cond),
-                global_cond_type=1 if self.global_cond_type == "adaLN" else 0, patch_size=self.patch_size,
+                global_cond_type=1 if self.global_cond_type == "adaLN" else 0, patch_size=1,
                 operand_dtype=1 if self.operand_dtype == "bf16" else 0)
             h = ctypes.c_void_p()
             _native.check(lib.satb_dit_create(ctypes.byref(cfg), ctypes.byref(h)))
@@ -136,6 +142,9 @@ class DiffusionTransformer(nn.Module):
                             f"parameter {name} is on {t.device}: move the model to a CUDA device "
                             "(this package has no CPU path)")
                     src = t.detach().to(torch.float32).contiguous()
+                    if self.patch_size > 1 and name in ("preprocess_conv.weight", "postprocess_conv.weight"):
+                        eye = torch.eye(self.patch_size, device=src.device, dtype=src.dtype)
+                        src = torch.kron(src[:, :, 0], eye).unsqueeze(-1).contiguous()
                     _native.check(lib.satb_dit_load_weight(self.__dict__["_h"], name.encode(), _native.ptr(src),
                                                            src.numel(), st))
                 _native.check(lib.satb_dit_finalize(self.__dict__["_h"], st))
@@ -193,6 +202,23 @@ class DiffusionTransformer(nn.Module):
                 else:
                     self.__dict__["_neg_masked"] = ((self._tkey(negative_cross_attn_cond),
                                                      self._tkey(negative_cross_attn_mask)), neg)
+        p = self.patch_size
+        if p > 1:
+            if x.shape[2] % p != 0:
+                raise ValueError(f"sequence length {x.shape[2]} is not a multiple of patch_size {p}")
+            if use_cfg and scale_phi != 0.0:
+                # the std rescale (dit.py:342-345) is over the un-patched channels: take the combined and the
+                # conditional outputs from two native calls and rescale here (device tensors, torch elementwise)
+                kw = dict(cross_attn_cond=cross_attn_cond, cross_attn_cond_mask=cross_attn_cond_mask,
+                          negative_cross_attn_cond=negative_cross_attn_cond,
+                          negative_cross_attn_mask=negative_cross_attn_mask, global_embed=global_embed)
+                cfg_out = self.forward(x, t, cfg_scale=cfg_scale, scale_phi=0.0, **kw)
+                cond_out = self.forward(x, t, cfg_scale=1.0, scale_phi=0.0, **kw)
+                rescaled = cfg_out * (cond_out.std(dim=1, keepdim=True) / cfg_out.std(dim=1, keepdim=True))
+                out = scale_phi * rescaled + (1 - scale_phi) * cfg_out
+                return (out, {"hidden_states": []}) if return_info else out
+            b_, c_, l_ = x.shape
+            x = x.reshape(b_, c_, l_ // p, p).transpose(2, 3).reshape(b_, c_ * p, l_ // p)   # channel = c * p + pi
         h = self._handle(x.device)
         B, C, L = x.shape
         self._prepare(h, cross_attn_cond, neg, global_embed, use_cfg, x.device, B)
@@ -208,7 +234,14 @@ class DiffusionTransformer(nn.Module):
                                                                _native.ptr(hidden), B, L, float(cfg_scale),
                                                                float(scale_phi), st))
             info = {"hidden_states": [hidden.view(-1, L + P, self.embed_dim)]}
-            return out.to(x.dtype), info
+            return self._unpatch(out).to(x.dtype), info
         _native.check(_native.lib().satb_dit_forward(h, _native.ptr(xin), _native.ptr(tin), _native.ptr(out), B, L,
                                                      float(cfg_scale), float(scale_phi), st))
-        return out.to(x.dtype)
+        return self._unpatch(out).to(x.dtype)
+
+    def _unpatch(self, out):
+        p = self.patch_size
+        if p == 1:
+            return out
+        b, cp, tt = out.shape                                     # "b (c p) t -> b c (t p)"
+        return out.reshape(b, cp // p, p, tt).transpose(2, 3).reshape(b, cp // p, tt * p)

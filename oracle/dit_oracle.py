@@ -173,7 +173,8 @@ def _mlp(x, sd, name):
 
 def dit_inner_forward(sd, cfg, x, t, cross_attn_cond=None, global_embed=None, hidden_states=None):
     """models/dit.py:135-226 (``_forward``), continuous_transformer backbone,
-    patch_size 1, no input_concat / prepend_cond."""
+    optional patching (dit.py:206-207,221-222), no input_concat / prepend_cond."""
+    patch = cfg.get("patch_size", 1)
     depth = cfg["depth"]
     dim_heads = cfg["embed_dim"] // cfg["num_heads"]
     gtype = cfg.get("global_cond_type", "prepend")
@@ -190,10 +191,16 @@ def dit_inner_forward(sd, cfg, x, t, cross_attn_cond=None, global_embed=None, hi
         prepend_length = 1
     x = F.conv1d(x, sd["preprocess_conv.weight"]) + x                            # dit.py:197
     x = x.transpose(1, 2)
+    if patch > 1:                                                                # "b (t p) c -> b t (c p)"
+        b, tp, c = x.shape
+        x = x.reshape(b, tp // patch, patch, c).transpose(2, 3).reshape(b, tp // patch, c * patch)
     out = continuous_transformer(x, prepend, cross_attn_cond,
                                  global_embed if gtype == "adaLN" else None,
                                  sd, depth, dim_heads, hidden_states)
     out = out.transpose(1, 2)[:, :, prepend_length:]                             # dit.py:219
+    if patch > 1:                                                                # "b (c p) t -> b c (t p)"
+        b, cp, tt = out.shape
+        out = out.reshape(b, cp // patch, patch, tt).transpose(2, 3).reshape(b, cp // patch, tt * patch)
     return F.conv1d(out, sd["postprocess_conv.weight"]) + out                    # dit.py:224
 
 
@@ -236,6 +243,7 @@ def dit_param_shapes(cfg):
     reference state-dict layout."""
     D = cfg["embed_dim"]
     io = cfg["io_channels"]
+    iop = io * cfg.get("patch_size", 1)
     ct = cfg.get("cond_token_dim", 0)
     gd = cfg.get("global_cond_dim", 0)
     cond_embed = D if cfg.get("project_cond_tokens", True) else ct
@@ -246,7 +254,7 @@ def dit_param_shapes(cfg):
         "to_timestep_embed.0.weight": (D, 256), "to_timestep_embed.0.bias": (D,),
         "to_timestep_embed.2.weight": (D, D), "to_timestep_embed.2.bias": (D,),
         "preprocess_conv.weight": (io, io, 1), "postprocess_conv.weight": (io, io, 1),
-        "transformer.project_in.weight": (D, io), "transformer.project_out.weight": (io, D),
+        "transformer.project_in.weight": (D, iop), "transformer.project_out.weight": (iop, D),
         "transformer.rotary_pos_emb.inv_freq": (max(dh // 2, 32) // 2,),
     }
     if ct > 0:
