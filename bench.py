@@ -336,29 +336,13 @@ def run_native(args):
     ms_per_step = elapsed_ms / args.steps
     value = world * args.steps / (elapsed_ms / 1e3)
 
-    # ---------------- same K steps again with per-kernel-class CUDA events (roofline) ---------
-    # (a second pass: event records between kernels would defeat the programmatic dependent
-    # launches the timed region above benefits from)
-    _native.check(lib.satb_dit_profile(h_dit, 1))
-    _native.check(lib.satb_dit_profile_read(h_dit, ms8, cnt8))   # clear
-    barrier()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for _ in range(args.steps):
-        loop.step()
-    p1.record()
-    barrier()
-    profiled_ms_per_step = p0.elapsed_time(p1) / args.steps
-    _native.check(lib.satb_dit_profile_read(h_dit, ms8, cnt8))
-    _native.check(lib.satb_dit_profile(h_dit, 0))
-
     # ---------------- e2e: same steps through the public call with HOST buffers --------------
     x_host = torch.empty(BATCH, 64, LATENT_LEN, pin_memory=True).copy_(loop.x.cpu())
     out_host = torch.empty(BATCH, 64, LATENT_LEN, pin_memory=True)
     x_dev = torch.empty(BATCH, 64, LATENT_LEN, device=device)
     loop2 = Loop()
     loop2.d1, loop2.d2, loop2.h1, loop2.h2, loop2.i = loop.d1, loop.d2, loop.h1, loop.h2, loop.i
-    for _ in range(2):
+    for _ in range(max(args.warmup, 3)):
         x_dev.copy_(x_host, non_blocking=True)
         out_host.copy_(loop2.step(x_dev), non_blocking=True)
     barrier()
@@ -376,6 +360,33 @@ def run_native(args):
         e2e_ms = float(tmax.item())
     e2e_value = world * args.steps / (e2e_ms / 1e3)
     io_bytes = BATCH * 64 * LATENT_LEN * 4
+
+    # host-side cost of enqueueing one step (launch queue empty before, no sync after): how far the
+    # GPU-bound numbers above are from being launch-bound on this box's host
+    host_ms = []
+    for _ in range(5):
+        torch.cuda.synchronize()
+        h0 = time.perf_counter()
+        loop.step()
+        host_ms.append((time.perf_counter() - h0) * 1e3)
+    barrier()
+    host_enqueue_ms = sorted(host_ms)[len(host_ms) // 2]
+
+    # ---------------- same K steps again with per-kernel-class CUDA events (roofline) ---------
+    # (a second pass: event records between kernels would defeat the programmatic dependent
+    # launches the timed region above benefits from)
+    _native.check(lib.satb_dit_profile(h_dit, 1))
+    _native.check(lib.satb_dit_profile_read(h_dit, ms8, cnt8))   # clear
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(args.steps):
+        loop.step()
+    p1.record()
+    barrier()
+    profiled_ms_per_step = p0.elapsed_time(p1) / args.steps
+    _native.check(lib.satb_dit_profile_read(h_dit, ms8, cnt8))
+    _native.check(lib.satb_dit_profile(h_dit, 0))
 
     # ---------------- Oobleck decode of the batch (audio-seconds/s of a full generation) ------
     lat = loop.x / max(float(loop.x.abs().max()), 1.0)
@@ -471,7 +482,7 @@ def run_native(args):
                      "traffic": 125806592, "traffic_unit": "bytes per launch (ncu)", "peak_source": peak_src,
                      "avg_launch_ms": ff_in_ms},
         "step_tflops": step_tflops, "step_frac_of_peak": step_tflops / peak_tf,
-        "profiled_pass_ms_per_step": profiled_ms_per_step,
+        "profiled_pass_ms_per_step": profiled_ms_per_step, "host_enqueue_ms_per_step": host_enqueue_ms,
         "kernel_breakdown": breakdown,
         "decode_ms_batch": decode_ms, "audio_sec_per_s_100step": audio_sec_per_s,
         "other_shapes": extra_shapes,
