@@ -175,7 +175,7 @@ def run_reference(args):
             "config": config_dict(args),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------- native arm
@@ -495,12 +495,30 @@ def run_native(args):
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg()
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist:
         td.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _reserve_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes its version banner to
+    fd 1), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a private duplicate."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

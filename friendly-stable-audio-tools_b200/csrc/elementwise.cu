@@ -21,8 +21,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 // One warp per row, the row lives in registers (two-pass mean / variance).
 constexpr int kLnMaxVec = 16;  // D <= 16 * 128 = 2048
 
-template <bool BF16>
-__global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+// NV = float4 per lane held in registers (D <= NV * 128).  The kernel is bound by memory-level parallelism
+// (ncu: 12 long-scoreboard stalls per issue, 20 resident warps with the old 16-deep register array), so the
+// array is sized to the actual row and the register count capped for 8 blocks = 32 rows in flight per SM.
+template <bool BF16, int NV>
+__global__ void __launch_bounds__(128, NV <= 8 ? 8 : (NV <= 12 ? 7 : 5)) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, uint16_t* __restrict__ out,
                                                         int rows, int D, const float* __restrict__ scale,
                                                         const float* __restrict__ shift, int64_t mod_stride,
@@ -34,10 +37,10 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
   if (row >= rows) return;
   const int nv = D >> 7;  // float4 per lane
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
-  float4 v[kLnMaxVec];
+  float4 v[NV];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     if (i < nv) {
       v[i] = xr[lane + 32 * i];
       sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -46,7 +49,7 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
   const float mean = warp_sum(sum) / static_cast<float>(D);
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     if (i < nv) {
       const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
       sq += (a * a + b * b) + (c * c + d * d);
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
   }
   uint2* o2 = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * D);
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     if (i < nv) {
       const int idx = lane + 32 * i;
       const float4 g = __ldg(g4 + idx);
@@ -340,12 +343,20 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, void
   if (rows <= 0) return 0;
   const int grid = ceil_div(rows, 4);
   const int items = n_items > 0 ? n_items : 1;
+  const int nv = D >> 7;
+  auto go = [&](auto kern) -> int {
+    SATB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(128), 0, stream, x, gamma, beta, static_cast<uint16_t*>(out16), rows,
+                               D, scale, shift, mod_stride, rows_per_item, items));
+    return 0;
+  };
+  int rc;
   if (bf16)
-    SATB_CHECK_CUDA(launch_pdl(layernorm_kernel<true>, dim3(grid), dim3(128), 0, stream, x, gamma, beta,
-                               static_cast<uint16_t*>(out16), rows, D, scale, shift, mod_stride, rows_per_item, items));
+    rc = nv <= 4 ? go(layernorm_kernel<true, 4>) : nv <= 8 ? go(layernorm_kernel<true, 8>)
+         : nv <= 12 ? go(layernorm_kernel<true, 12>) : go(layernorm_kernel<true, 16>);
   else
-    SATB_CHECK_CUDA(launch_pdl(layernorm_kernel<false>, dim3(grid), dim3(128), 0, stream, x, gamma, beta,
-                               static_cast<uint16_t*>(out16), rows, D, scale, shift, mod_stride, rows_per_item, items));
+    rc = nv <= 4 ? go(layernorm_kernel<false, 4>) : nv <= 8 ? go(layernorm_kernel<false, 8>)
+         : nv <= 12 ? go(layernorm_kernel<false, 12>) : go(layernorm_kernel<false, 16>);
+  SATB_PROPAGATE(rc);
   count_launch();
   return 0;
 }
