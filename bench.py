@@ -390,15 +390,17 @@ def run_native(args):
 
     # ---------------- Oobleck decode of the batch (audio-seconds/s of a full generation) ------
     lat = loop.x / max(float(loop.x.abs().max()), 1.0)
-    audio = dec(lat[:1])
+    for _ in range(3):
+        audio = dec(lat[:1])
     barrier()
     d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     d0.record()
-    for b in range(BATCH):                       # one item at a time, like the reference's iterate_batch
-        audio = dec(lat[b:b + 1])
+    for _ in range(3):                           # three passes over the batch; the mean pass is reported
+        for b in range(BATCH):                   # one item at a time, like the reference's iterate_batch
+            audio = dec(lat[b:b + 1])
     d1.record()
     torch.cuda.synchronize()
-    decode_ms = d0.elapsed_time(d1)
+    decode_ms = d0.elapsed_time(d1) / 3
     if dist:
         tmax = torch.tensor([decode_ms], device=device)
         td.all_reduce(tmax, op=td.ReduceOp.MAX)

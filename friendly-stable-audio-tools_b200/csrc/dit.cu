@@ -79,8 +79,12 @@ static int linear(TmapCache& tc, const void* A, int64_t lda, int M, int K, const
   SATB_PROPAGATE(tc.get_a(A, K, M, 1, lda, static_cast<int64_t>(M) * lda, &ta));
   GemmShape s;
   s.L = M; s.batches = 1; s.N = N; s.K = K; s.n_taps = 1; s.tap_base = 0; s.tap_step = 0; s.b_tap_rows = N; s.stride = 1;
-  if constexpr (BN == 256) {
-    // CTA-pair kernel for the large GEMMs (256 x 256 tiles, half of B per CTA)
+  s.b_static = 1;   // W is a weight matrix prepared at finalize time
+  if constexpr (BN == 256 || BN == 128) {
+    // CTA-pair kernel (256 x BN tiles, half of B per CTA).  Also for BN = 128: a single CTA streaming
+    // 128 x 128 x 16 MMAs needs 128 B/clk of shared-memory operand reads, the SM's limit; the pair needs 96.
+    // (Choosing single CTAs where they save a round of the persistent grid -- QKV: 594 pair tiles = 8.03 -> 9
+    // rounds vs 1170 single tiles = 7.9 -> 8 -- was measured ~3 % slower: the pair's lower smem traffic wins.)
     if (gemm_use_2cta() && M >= 1024) {
       SATB_PROPAGATE(tc.get_b(W, K, N, K, BN / 2, &tb));
       return launch_gemm_2cta<Epi, BN, BF16>(*ta, *tb, s, ep, stream);

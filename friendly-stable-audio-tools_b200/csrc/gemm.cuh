@@ -33,6 +33,8 @@ struct GemmShape {
   int b_tap_rows;   // rows of B per tap (= N as stored)
   int stride;       // >1: strided conv; tap position u = l*stride + tap_base + tap*tap_step is
                     // addressed as (phase = u mod stride, row = u div stride) of the 4-D map
+  int b_static = 0; // 1: B holds long-lived weights that no kernel still running can be writing, so its first
+                    // tiles may be fetched before the programmatic-dependency wait
 };
 
 constexpr int kBlockM = 128;
@@ -112,11 +114,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();   // the next kernel may be scheduled as SMs drain
-  pdl_wait();                // everything above overlapped the previous kernel's tail
+  // Everything above overlapped the previous kernel's tail.  The B operand (weights) never depends on the
+  // previous kernel, so the producer thread also starts the B loads of its first stages before it waits for
+  // the dependency; every other thread waits here.
+  const bool is_producer_warp = warp == 0;
+  if (!is_producer_warp) pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
       // ------------------------------------------------------------ TMA producer
+      int pre = 0;
+      if (s.b_static && static_cast<int>(blockIdx.x) < total_tiles) {
+        pre = num_kb < Cfg::kStages ? num_kb : Cfg::kStages;
+        const int n0 = (static_cast<int>(blockIdx.x) / tiles_per_n) * BN;
+        for (int kb = 0; kb < pre; ++kb) {
+          const int tap = kb / kb_per_tap;
+          const int k0 = (kb - tap * kb_per_tap) * kBlockK;
+          mbar_expect_tx(&full_bar[kb], Cfg::kStage);
+          tma_load_2d(smem + kb * Cfg::kStage + Cfg::kStageA, &tmB, &full_bar[kb], k0, tap * s.b_tap_rows + n0);
+        }
+      }
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -131,7 +149,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStage;
           uint8_t* sb = sa + Cfg::kStageA;
-          mbar_expect_tx(&full_bar[stage], Cfg::kStage);
+          const bool b_done = tile == static_cast<int>(blockIdx.x) && kb < pre;   // issued before the wait
+          if (!b_done) mbar_expect_tx(&full_bar[stage], Cfg::kStage);
           const int u = s.tap_base + tap * s.tap_step;
           int ph = 0, ro = u;
           if (s.stride > 1) {
@@ -139,7 +158,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ph = u - ro * s.stride;
           }
           tma_load_4d(sa, &tmA, &full_bar[stage], k0, ph, m0 + ro, batch);
-          tma_load_2d(sb, &tmB, &full_bar[stage], k0, tap * s.b_tap_rows + n0);
+          if (!b_done) tma_load_2d(sb, &tmB, &full_bar[stage], k0, tap * s.b_tap_rows + n0);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -322,11 +341,23 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
-  pdl_wait();
+  if (warp != 0) pdl_wait();   // the producer warp first prefetches weights (see the single-CTA kernel)
 
   if (warp == 0) {
     if (elect_one()) {
       // ------------------------------------------------------ TMA producer (both CTAs)
+      int pre = 0;
+      if (s.b_static && cluster_id < total_tiles) {
+        pre = num_kb < Cfg::kStages ? num_kb : Cfg::kStages;
+        const int n0 = (cluster_id / tiles_per_n) * BN + rank * (BN / 2);
+        for (int kb = 0; kb < pre; ++kb) {
+          const int tap = kb / kb_per_tap;
+          const int k0 = (kb - tap * kb_per_tap) * kBlockK;
+          if (rank == 0) mbar_expect_tx(&full_bar[kb], 2 * Cfg::kStage);
+          tma_load_2d_2sm(smem + kb * Cfg::kStage + Cfg::kStageA, &tmB, &full_bar[kb], k0, tap * s.b_tap_rows + n0);
+        }
+      }
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
@@ -341,7 +372,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStage;
           uint8_t* sb = sa + Cfg::kStageA;
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStage);
+          const bool b_done = tile == cluster_id && kb < pre;
+          if (rank == 0 && !b_done) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStage);
           const int u = s.tap_base + tap * s.tap_step;
           int ph = 0, ro = u;
           if (s.stride > 1) {
@@ -349,7 +381,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             ph = u - ro * s.stride;
           }
           tma_load_4d_2sm(sa, &tmA, &full_bar[stage], k0, ph, m0 + ro, batch);
-          tma_load_2d_2sm(sb, &tmB, &full_bar[stage], k0, tap * s.b_tap_rows + n0);
+          if (!b_done) tma_load_2d_2sm(sb, &tmB, &full_bar[stage], k0, tap * s.b_tap_rows + n0);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;

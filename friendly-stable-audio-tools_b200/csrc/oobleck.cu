@@ -311,6 +311,7 @@ int run_conv_gemm(SatbOobleck* h, const ConvW& cw, const void* in16, int B, int 
                   const typename Epi::Params& ep, cudaStream_t st) {
   GemmShape s;
   s.batches = B;
+  s.b_static = 1;   // folded weight-norm weights, written at finalize time
   s.K = cw.cin;
   int a_stride = 1, a_rows = L_in;
   if (kind == 0) {
