@@ -72,7 +72,7 @@ def test_dit_repeat_call_is_deterministic_and_cache_safe():
     assert rel_l2(y4.cpu(), y1.cpu()) < 1e-6
 
 
-@pytest.mark.parametrize("depth,B,cfg_scale", [(2, 1, 7.0), (1, 2, 1.0)])
+@pytest.mark.parametrize("depth,B,cfg_scale", [(2, 1, 7.0), (1, 2, 1.0), (1, 4, 3.0)])   # last = the bench shape: 8 rows
 def test_dit_full_width_vs_oracle(depth, B, cfg_scale):
     """SA-Open-1.0 width (D=1536, 24 heads, 130x768 context, N=1025 tokens) at reduced depth,
     against the CPU oracle computed live (fp32)."""
@@ -134,3 +134,23 @@ def test_dit_full_width_bf16_vs_oracle():
     y = build_native_dit(cfg, sd, operand_dtype="bf16")(x.cuda(), t.cuda(), cross_attn_cond=c.cuda(),
                                                         global_embed=ge.cuda(), cfg_scale=1.0).cpu()
     assert rel_l2(y, ref) < 1.5e-2
+
+
+
+def test_dit_full_size_cfg_is_linear_in_the_scale_and_deterministic():
+    """BASELINE-size property test (SA-Open-1.0, all 24 blocks, 1025 tokens; no oracle at this size):
+    out(s) = u + (c - u) s is affine in the guidance scale, so out(5) - out(1) == 2 (out(3) - out(1)), the
+    no-CFG output equals out(1), and repeated calls are bit-identical."""
+    from oracle import dit_oracle as do
+    sd = do.make_dit_weights(SAO_DIT, seed=10)
+    m = build_native_dit(SAO_DIT, sd)
+    g = torch.Generator().manual_seed(4)
+    x, t = torch.randn(1, 64, 1024, generator=g).cuda(), torch.tensor([0.45]).cuda()
+    c, ge = torch.randn(1, 130, 768, generator=g).cuda(), torch.randn(1, 1536, generator=g).cuda()
+    run = lambda s: m(x, t, cross_attn_cond=c, global_embed=ge, cfg_scale=s).float()
+    y1, y3, y5, y3b = run(1.0), run(3.0), run(5.0), run(3.0)
+    assert torch.isfinite(y5).all()
+    assert torch.equal(y3, y3b)
+    d31, d51 = y3 - y1, y5 - y1
+    assert rel_l2(d51, 2.0 * d31) < 1e-3
+    assert float(d31.norm()) > 1e-3 * float(y1.norm())          # guidance really changes the output
