@@ -375,6 +375,19 @@ int residual_unit(SatbOobleck* h, const std::string& pfx, int C, int B, int L, i
     std::swap(sA, sT);
     return 0;
   }
+  if (C == ResUnit256Cfg::kC && c7.k == ResUnit256Cfg::kTaps && dil <= ResUnit256Cfg::kMaxDil && L >= 512 &&
+      gemm_use_2cta() && resunit_use_fused()) {
+    const CUtensorMap *ta, *tb7, *tb1;
+    SATB_PROPAGATE(get_tmap_a(h, sA, C, L, B, L, 1, &ta, ResUnit256Cfg::halo_rows(dil)));
+    SATB_PROPAGATE(get_tmap_b(h, c7, c7.k * C, 128, &tb7));
+    SATB_PROPAGATE(get_tmap_b(h, c1, C, 128, &tb1));
+    e1.s16_out = sT;
+    ResUnitParams<BF16> rp{c7.bias, s2.a, s2.ib, e1};
+    ResUnitShape rs{L, B, dil};
+    SATB_PROPAGATE(launch_resunit256<BF16>(*ta, *tb7, *tb1, rs, rp, st));
+    std::swap(sA, sT);
+    return 0;
+  }
   // conv7(dil) on sA -> snake2 -> sT ; conv1 on sT -> + x -> raw, snake_next -> sA
   typename E::Params e7{c7.bias, nullptr, nullptr, sT, s2.a, s2.ib, C, L, 1, 0};
   SATB_PROPAGATE((run_conv_gemm<E, BF16>(h, c7, sA, B, L, 0, dil, 1, e7, st)));

@@ -365,4 +365,332 @@ int launch_resunit(const CUtensorMap& tmA, const CUtensorMap& tmB7, const CUtens
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 256-channel variant.  Same algorithm; differences forced by the resources of one SM:
+//   * both accumulators are 256 TMEM columns, so neither is double-buffered: the tensor pipe idles while the
+//     epilogue turns acc1 into the smem tile (phase A), and the epilogue of tile t (phase B) overlaps conv7(t+1);
+//   * the 1x1 weights (64 KB per CTA) do not stay resident: they stream through the same B ring, four
+//     16 KB tiles per output tile, after the 28 conv7 weight tiles;
+//   * A ring 2 x 23 KB, B ring 4 x 16 KB, smem tile 64 KB, 8 epilogue warps with four 32-column chunks each.
+struct ResUnit256Cfg {
+  static constexpr int kC = 256;
+  static constexpr int kTaps = 7;
+  static constexpr int kMaxDil = 9;
+  static constexpr int kKb = kC / kBlockK;                                         // 4 k-blocks
+  static constexpr int kSlotA = ((kBlockM + (kTaps - 1) * kMaxDil) * 128 + 1023) / 1024 * 1024;
+  static constexpr int kStagesA = 2;
+  static constexpr int kTileB = (kC / 2) * kBlockK * 2;                            // 16 KB
+  static constexpr int kStagesB = 4;
+  static constexpr int kTileA2 = kBlockM * kBlockK * 2;                            // 16 KB per k-block
+  static constexpr int kOffB = kStagesA * kSlotA;
+  static constexpr int kOffA2 = kOffB + kStagesB * kTileB;
+  static constexpr int kOffBars = kOffA2 + kKb * kTileA2;
+  static constexpr int kOffParams = kOffBars + 512;
+  static constexpr int kOffEpiStage = kOffParams + 3 * kC * 4;
+  static constexpr int kEpiStage = 32 * 36 * 4;
+  static constexpr int kSmemBytes = kOffEpiStage + kEpiWarps * kEpiStage + 1024;
+  static constexpr int kTmemCols = 512;
+  static_assert(kSmemBytes <= 227 * 1024, "smem budget");
+  static_assert(kOffB % 1024 == 0 && kOffA2 % 1024 == 0, "swizzled tiles must be 1024-byte aligned");
+  __host__ __device__ static int halo_rows(int dil) { return kBlockM + (kTaps - 1) * dil; }
+};
+
+template <bool BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+resunit256_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB7,
+                               const __grid_constant__ CUtensorMap tmB1, const ResUnitShape s,
+                               const ResUnitParams<BF16> ep) {
+  using Cfg = ResUnit256Cfg;
+  using Epi = EpiConv<BF16>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bs = smem + Cfg::kOffB;
+  uint8_t* a2s = smem + Cfg::kOffA2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBars);
+  uint64_t* a_full = bars;                           // [2] CTA 0
+  uint64_t* a_empty = a_full + Cfg::kStagesA;        // [2] per CTA
+  uint64_t* b_full = a_empty + Cfg::kStagesA;        // [4] CTA 0
+  uint64_t* b_empty = b_full + Cfg::kStagesB;        // [4] per CTA
+  uint64_t* acc1_full = b_empty + Cfg::kStagesB;     // per CTA, multicast commit
+  uint64_t* a2_full = acc1_full + 1;                 // CTA 0, 2 arrivals (forwarders)
+  uint64_t* a2_local = a2_full + 1;                  // per CTA, 8 arrivals
+  uint64_t* a2_empty = a2_local + 1;                 // per CTA, multicast commit of G2
+  uint64_t* acc2_full = a2_empty + 1;                // per CTA, multicast commit
+  uint64_t* acc2_empty = acc2_full + 1;              // CTA 0, 16 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
+  float* prm = reinterpret_cast<float*>(smem + Cfg::kOffParams);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int m_tiles = (s.L + 2 * kBlockM - 1) / (2 * kBlockM);
+  const int total_tiles = m_tiles * s.batches;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB7);
+    tma_prefetch_desc(&tmB1);
+    for (int i = 0; i < Cfg::kStagesA; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < Cfg::kStagesB; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    mbar_init(acc1_full, 1);
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, 2 * kEpiWarps);
+    mbar_init(a2_full, 2);
+    mbar_init(a2_local, kEpiWarps);
+    mbar_init(a2_empty, 1);
+    fence_mbar_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + 3 * 64) {     // 192 threads x float4 = 3 x 256 floats
+    const int i = threadIdx.x - 128;
+    const float* src = i < 64 ? ep.bias7 : (i < 128 ? ep.sn2_a : ep.sn2_ib);
+    reinterpret_cast<float4*>(prm)[i] =
+        src ? __ldg(reinterpret_cast<const float4*>(src) + (i & 63)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ------------------------------------------------------ TMA producer (both CTAs)
+      const int a_tx = Cfg::halo_rows(s.dil) * 128;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      auto load_b = [&](const CUtensorMap* tm, int k0, int row0) {
+        mbar_wait(&b_empty[sb], pb ^ 1);
+        if (rank == 0) mbar_expect_tx(&b_full[sb], 2 * Cfg::kTileB);
+        tma_load_2d_2sm(bs + sb * Cfg::kTileB, tm, &b_full[sb], k0, row0);
+        if (++sb == Cfg::kStagesB) {
+          sb = 0;
+          pb ^= 1;
+        }
+      };
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        const int batch = tile / m_tiles;
+        const int m0 = (tile - batch * m_tiles) * 2 * kBlockM + rank * kBlockM;
+        for (int kb = 0; kb < Cfg::kKb; ++kb) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          if (rank == 0) mbar_expect_tx(&a_full[sa], 2 * a_tx);
+          tma_load_4d_2sm(smem + sa * Cfg::kSlotA, &tmA, &a_full[sa], kb * kBlockK, 0, m0 - 3 * s.dil, batch);
+          if (++sa == Cfg::kStagesA) {
+            sa = 0;
+            pa ^= 1;
+          }
+          for (int tap = 0; tap < Cfg::kTaps; ++tap) load_b(&tmB7, kb * kBlockK, tap * Cfg::kC + rank * (Cfg::kC / 2));
+        }
+        for (int kb = 0; kb < Cfg::kKb; ++kb) load_b(&tmB1, kb * kBlockK, rank * (Cfg::kC / 2));   // 1x1 weights
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      // ------------------------------------------------------ MMA issuer (CTA 0 for the pair)
+      constexpr uint32_t idesc = make_idesc_f16(2 * kBlockM, Cfg::kC, BF16);
+      const uint32_t a2_addr = smem_u32(a2s), b_addr0 = smem_u32(bs);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      const uint32_t tap_bytes = s.dil * 128;
+      const uint32_t acc1 = tmem_base, acc2 = tmem_base + Cfg::kC;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+        // acc1 is free: phase A of the previous tile was observed (a2_full) before its G2 was issued
+        for (int kb = 0; kb < Cfg::kKb; ++kb) {
+          mbar_wait(&a_full[sa], pa);
+          const uint32_t a_addr = smem_u32(smem + sa * Cfg::kSlotA);
+          for (int tap = 0; tap < Cfg::kTaps; ++tap) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint32_t a_tap = a_addr + tap * tap_bytes;
+            const uint32_t b_addr = b_addr0 + sb * Cfg::kTileB;
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_f16_ss_2sm(acc1, make_desc_kmajor_sw128(a_tap + k * kUmmaK * 2),
+                              make_desc_kmajor_sw128(b_addr + k * kUmmaK * 2), idesc, (kb | tap | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&b_empty[sb]);
+            if (++sb == Cfg::kStagesB) {
+              sb = 0;
+              pb ^= 1;
+            }
+          }
+          umma_commit_2sm(&a_empty[sa]);
+          if (++sa == Cfg::kStagesA) {
+            sa = 0;
+            pa ^= 1;
+          }
+        }
+        umma_commit_2sm(acc1_full);
+        // G2(it): 1x1 convolution from the smem tile, weights streamed through the B ring
+        mbar_wait_cluster(a2_full, it & 1);
+        mbar_wait(acc2_empty, (it & 1) ^ 1);
+        for (int kb = 0; kb < Cfg::kKb; ++kb) {
+          mbar_wait(&b_full[sb], pb);
+          tc_fence_after();
+          const uint32_t b_addr = b_addr0 + sb * Cfg::kTileB;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_f16_ss_2sm(acc2, make_desc_kmajor_sw128(a2_addr + kb * Cfg::kTileA2 + k * kUmmaK * 2),
+                            make_desc_kmajor_sw128(b_addr + k * kUmmaK * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&b_empty[sb]);
+          if (++sb == Cfg::kStagesB) {
+            sb = 0;
+            pb ^= 1;
+          }
+        }
+        umma_commit_2sm(a2_empty);
+        umma_commit_2sm(acc2_full);
+      }
+    }
+  } else if (warp == 3) {
+    if (elect_one()) {
+      // ------------------------------------------------------ forwarder (both CTAs), see the 128-channel kernel
+      int it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+        mbar_wait(a2_local, it & 1);
+        mbar_arrive_remote_cluster(a2_full, 0);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (both CTAs)
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;              // chunks half, half + 2, half + 4, half + 6 of the 8
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float* stage_buf = reinterpret_cast<float*>(smem + Cfg::kOffEpiStage + (warp - 4) * Cfg::kEpiStage);
+
+    auto chunk_a = [&](int ci, const uint32_t (&r)[32]) {
+      uint32_t o[16];
+      const float* pb = prm + ci * 32;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const ulonglong2 b2 = *reinterpret_cast<const ulonglong2*>(pb + 4 * j);
+        const ulonglong2 a2 = *reinterpret_cast<const ulonglong2*>(pb + Cfg::kC + 4 * j);
+        const ulonglong2 i2 = *reinterpret_cast<const ulonglong2*>(pb + 2 * Cfg::kC + 4 * j);
+        const uint64_t acc01 = (static_cast<uint64_t>(r[4 * j + 1]) << 32) | r[4 * j];
+        const uint64_t acc23 = (static_cast<uint64_t>(r[4 * j + 3]) << 32) | r[4 * j + 2];
+        float v0, v1, v2, v3;
+        f2_unpack(snake_fast2(f2_add(acc01, b2.x), a2.x, i2.x), v0, v1);
+        f2_unpack(snake_fast2(f2_add(acc23, b2.y), a2.y, i2.y), v2, v3);
+        o[2 * j] = Op16<BF16>::pack(v0, v1);
+        o[2 * j + 1] = Op16<BF16>::pack(v2, v3);
+      }
+      uint8_t* rowp = a2s + (ci >> 1) * Cfg::kTileA2 + row * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c16 = ((ci & 1) * 4 + j) ^ (row & 7);
+        *reinterpret_cast<uint4*>(rowp + c16 * 16) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      }
+    };
+    auto make_ctx = [&](int batch, int m0, int ci) {
+      EpiCtx c;
+      c.l = m0 + row;
+      c.batch = batch;
+      c.row = batch * s.L + c.l;
+      c.valid = c.l < s.L;
+      c.l0 = m0 + q * 32;
+      c.L = s.L;
+      c.lane = lane;
+      c.stage = stage_buf;
+      c.col0 = ci * 32;
+      return c;
+    };
+
+    int it = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+      const int batch = tile / m_tiles;
+      const int m0 = (tile - batch * m_tiles) * 2 * kBlockM + rank * kBlockM;
+      // ---- phase A: acc1 -> + bias7 -> snake2 -> 16-bit -> swizzled smem tile
+      mbar_wait(acc1_full, it & 1);
+      tc_fence_after();
+      {
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(t_lane + half * 32, ra);
+        tmem_ld_32x32(t_lane + (half + 2) * 32, rb);
+        if (it > 0) mbar_wait(a2_empty, (it - 1) & 1);   // G2 of the previous tile has consumed the smem tile
+        tmem_ld_wait();
+        chunk_a(half, ra);
+        tmem_ld_32x32(t_lane + (half + 4) * 32, ra);
+        chunk_a(half + 2, rb);
+        tmem_ld_32x32(t_lane + (half + 6) * 32, rb);
+        tmem_ld_wait();
+        chunk_a(half + 4, ra);
+        chunk_a(half + 6, rb);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a2_local);
+      // ---- phase B: acc2 -> EpiConv (bias, skip, raw, snake_next); overlaps conv7 of the next tile
+      {
+        float4 rs0[8], rs1[8];
+        uint32_t r[32];
+        Epi::prefetch(ep.out, make_ctx(batch, m0, half), rs0);
+        mbar_wait(acc2_full, it & 1);
+        tc_fence_after();
+        const uint32_t t_row = t_lane + Cfg::kC;
+        tmem_ld_32x32(t_row + half * 32, r);
+        Epi::prefetch(ep.out, make_ctx(batch, m0, half + 2), rs1);
+        tmem_ld_wait();
+        Epi::finish(ep.out, make_ctx(batch, m0, half), r, rs0);
+        tmem_ld_32x32(t_row + (half + 2) * 32, r);
+        Epi::prefetch(ep.out, make_ctx(batch, m0, half + 4), rs0);
+        tmem_ld_wait();
+        Epi::finish(ep.out, make_ctx(batch, m0, half + 2), r, rs1);
+        tmem_ld_32x32(t_row + (half + 4) * 32, r);
+        Epi::prefetch(ep.out, make_ctx(batch, m0, half + 6), rs1);
+        tmem_ld_wait();
+        Epi::finish(ep.out, make_ctx(batch, m0, half + 4), r, rs0);
+        tmem_ld_32x32(t_row + (half + 6) * 32, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(acc2_empty, 0);   // accumulator fully in registers
+        Epi::finish(ep.out, make_ctx(batch, m0, half + 6), r, rs1);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// tmA: box rows = ResUnit256Cfg::halo_rows(s.dil); tmB7 / tmB1: 128-row boxes.
+template <bool BF16>
+int launch_resunit256(const CUtensorMap& tmA, const CUtensorMap& tmB7, const CUtensorMap& tmB1, const ResUnitShape& s,
+                      const ResUnitParams<BF16>& ep, cudaStream_t stream) {
+  using Cfg = ResUnit256Cfg;
+  SATB_REQUIRE(s.dil >= 1 && s.dil <= Cfg::kMaxDil, "resunit256: dilation out of range");
+  auto kern = resunit256_tcgen05_2cta_kernel<BF16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int total = ceil_div(s.L, 2 * kBlockM) * s.batches;
+  if (total <= 0) return 0;
+  int clusters = device_sm_count() / 2;
+  if (clusters > total) clusters = total;
+  SATB_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tmA, tmB7, tmB1, s, ep));
+  count_launch();
+  return 0;
+}
+
 }  // namespace satb

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 
 SAO_VAE = dict(channels=128, c_mults=[1, 2, 4, 8, 16], strides=[2, 4, 4, 8, 8], latent_dim=64, use_snake=True)
-CASES = [("dec", 1, 8), ("dec", 1, 24), ("dec", 2, 24), ("enc", 1, 24)]
+CASES = [("dec", 1, 8), ("dec", 2, 24), ("dec", 1, 320), ("enc", 1, 24), ("enc", 1, 160)]
 
 
 def run_child(tag):
@@ -46,7 +46,7 @@ def main():
         return
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     for tag, env in (("fused", {}), ("unfused", {"SATB_RESUNIT": "unfused"})):
-        subprocess.run([sys.executable, os.path.abspath(__file__), tag], env=dict(os.environ, **env), check=True, timeout=200)
+        subprocess.run([sys.executable, os.path.abspath(__file__), tag], env=dict(os.environ, **env), check=True, timeout=300)
     from oracle import oobleck_oracle as oo
     from helpers import rel_l2
     f = torch.load(os.path.join(ROOT, "gpurun_out", "resunit_fused.pt"))
