@@ -427,7 +427,7 @@ def run_native(args):
 
     # Oobleck decoder roofline bookkeeping, per sample of L = 1024 latents:
     #   FLOPs 5.163e12; bytes for the fusion level implemented (16-bit activated copy in/out of every
-    #   tensor-core conv, fp32 raw skip stream read+written once per ResidualUnit, the 128-channel
+    #   tensor-core conv, fp32 raw skip stream read+written once per ResidualUnit, the 128- and 256-channel
     #   ResidualUnits fused into one kernel):
     dec_flops = 5.163e12
     dec_bytes = 0.0
@@ -437,7 +437,7 @@ def run_native(args):
         elems = l_out * chans[i + 1]
         dec_bytes += 2.0 * l_in * chans[i] + 6.0 * elems        # ConvT: read s16, write raw fp32 + s16
         dec_bytes += (12 + 12 + 8) * elems                        # 3 x conv1 / fused unit: 2+4+4+2 B (last: no raw write)
-        if chans[i + 1] != 128:
+        if chans[i + 1] not in (128, 256):
             dec_bytes += 3 * 4.0 * elems                          # two-launch units: conv7 writes + conv1 reads a 16-bit copy
     dec_bytes += 2.0 * l_out * 128 + 4.0 * l_out * 2             # final conv
     dec_ms_sample = decode_ms / BATCH

@@ -16,7 +16,7 @@ import sys
 
 def layers(L, fused128=True):
     """(name, flops, algorithmic bytes) in launch order for the SA-Open-1.0 decoder.  With fused128 the
-    128-channel ResidualUnits are one launch each (resunit_tcgen05_2cta_kernel)."""
+    128- and 256-channel ResidualUnits are one launch each (resunit[256]_tcgen05_2cta_kernel)."""
     out = [("ncl->nlc16", 0, 64 * L * 6)]
     out.append(("conv_in k7 64->2048", 2 * L * 64 * 2048 * 7, L * (64 * 2 + 2048 * 6)))
     cin = 2048
@@ -24,7 +24,7 @@ def layers(L, fused128=True):
         lo = L * s
         out.append((f"convT s{s} {cin}->{cout}", 2 * L * cin * cout * 2 * s, L * cin * 2 + lo * cout * 6))
         for d in (1, 3, 9):
-            if fused128 and cout == 128:
+            if fused128 and cout in (128, 256):
                 out.append((f"  resunit d{d} {cout} (fused)", 2 * lo * cout * cout * 8, lo * cout * (2 + 4 + 4 + 2)))
                 continue
             out.append((f"  conv7 d{d} {cout}", 2 * lo * cout * cout * 7, lo * cout * 4))
