@@ -123,7 +123,7 @@ using namespace satb;
 struct SatbDit {
   SatbDitConfig cfg;
   int D, H, dh, C, ct, ce, gd, ge, ffi, depth, F, nf;
-  bool bf16, adaln;
+  bool bf16, adaln, qk_norm = false;
   int P;  // prepended tokens (1 in "prepend" mode, 0 in adaLN mode)
   std::vector<LayerW> layers;
   std::vector<void*> owned;   // every cudaMalloc of weight storage
@@ -204,6 +204,7 @@ int satb_dit_create(const SatbDitConfig* cfg, SatbDit** out) {
   d->nf = rot / 2;
   d->bf16 = cfg->operand_dtype == 1;
   d->adaln = cfg->global_cond_type == 1;
+  d->qk_norm = cfg->qk_norm != 0;
   d->P = d->adaln ? 0 : 1;
   if (d->ct > 0) {
     if (d->ce % 64 != 0 || d->H % (d->ce / 64) != 0) {
@@ -481,7 +482,13 @@ int satb_dit_prepare_cond(SatbDit* d, const float* cross, const float* neg_cross
       SATB_PROPAGATE((linear<E, 128, true>(d->tmaps, mid16, d->ce, Mr, d->ce, d->ce2_w, d->ce, E::Params{ce16, d->ce, nullptr, 0}, st)));
       for (int i = 0; i < d->depth; ++i) {
         uint16_t* kv = d->ws_kv.as<uint16_t>() + static_cast<size_t>(i) * rows * 2 * d->ce;
-        SATB_PROPAGATE((linear<E, 128, true>(d->tmaps, ce16, d->ce, Mr, d->ce, d->layers[i].w_kv, 2 * d->ce, E::Params{kv, 2 * d->ce, nullptr, 0}, st)));
+        if (d->qk_norm) {
+          typedef EpiHeadNorm16<true> EN;   // k heads normalised (transformer.py:433-436), v as is
+          SATB_PROPAGATE((linear<EN, 128, true>(d->tmaps, ce16, d->ce, Mr, d->ce, d->layers[i].w_kv, 2 * d->ce,
+                                                 EN::Params{kv, 2 * d->ce, d->ce, 0, 1, nullptr, nullptr}, st)));
+        } else {
+          SATB_PROPAGATE((linear<E, 128, true>(d->tmaps, ce16, d->ce, Mr, d->ce, d->layers[i].w_kv, 2 * d->ce, E::Params{kv, 2 * d->ce, nullptr, 0}, st)));
+        }
       }
     } else {
       typedef EpiStore16<false> E;
@@ -489,7 +496,13 @@ int satb_dit_prepare_cond(SatbDit* d, const float* cross, const float* neg_cross
       SATB_PROPAGATE((linear<E, 128, false>(d->tmaps, mid16, d->ce, Mr, d->ce, d->ce2_w, d->ce, E::Params{ce16, d->ce, nullptr, 0}, st)));
       for (int i = 0; i < d->depth; ++i) {
         uint16_t* kv = d->ws_kv.as<uint16_t>() + static_cast<size_t>(i) * rows * 2 * d->ce;
-        SATB_PROPAGATE((linear<E, 128, false>(d->tmaps, ce16, d->ce, Mr, d->ce, d->layers[i].w_kv, 2 * d->ce, E::Params{kv, 2 * d->ce, nullptr, 0}, st)));
+        if (d->qk_norm) {
+          typedef EpiHeadNorm16<false> EN;   // k heads normalised (transformer.py:433-436), v as is
+          SATB_PROPAGATE((linear<EN, 128, false>(d->tmaps, ce16, d->ce, Mr, d->ce, d->layers[i].w_kv, 2 * d->ce,
+                                                 EN::Params{kv, 2 * d->ce, d->ce, 0, 1, nullptr, nullptr}, st)));
+        } else {
+          SATB_PROPAGATE((linear<E, 128, false>(d->tmaps, ce16, d->ce, Mr, d->ce, d->layers[i].w_kv, 2 * d->ce, E::Params{kv, 2 * d->ce, nullptr, 0}, st)));
+        }
       }
     }
   }
@@ -558,9 +571,15 @@ static int dit_forward_impl(SatbDit* d, const float* x, const float* t, float* o
     }
     {
       ProfScope ps(d, PROF_QKV, st);
-      typedef EpiQkvRope<BF16> E;
-      typename E::Params ep{qkv, 3 * D, 2 * D, N_seq, cos_tab, sin_tab};
-      SATB_PROPAGATE((linear<E, 256, BF16>(d->tmaps, a16, D, M, D, W.w_qkv, 3 * D, ep, st)));
+      if (d->qk_norm) {
+        typedef EpiHeadNorm16<BF16> E;   // q, k heads L2-normalised, then rotary
+        typename E::Params ep{qkv, 3 * D, 2 * D, 2 * D, N_seq, cos_tab, sin_tab};
+        SATB_PROPAGATE((linear<E, 256, BF16>(d->tmaps, a16, D, M, D, W.w_qkv, 3 * D, ep, st)));
+      } else {
+        typedef EpiQkvRope<BF16> E;
+        typename E::Params ep{qkv, 3 * D, 2 * D, N_seq, cos_tab, sin_tab};
+        SATB_PROPAGATE((linear<E, 256, BF16>(d->tmaps, a16, D, M, D, W.w_qkv, 3 * D, ep, st)));
+      }
     }
     {
       ProfScope ps(d, PROF_ATTN_SELF, st);
@@ -579,7 +598,11 @@ static int dit_forward_impl(SatbDit* d, const float* x, const float* t, float* o
       ProfScope ps(d, PROF_CROSS, st);
       const int Hkv = d->ce / 64;
       SATB_PROPAGATE(launch_layernorm(h, W.ca_g, W.ca_b, a16, Mc, D, nullptr, nullptr, 0, N_seq, 1, BF16, st));
-      {
+      if (d->qk_norm) {
+        typedef EpiHeadNorm16<BF16> E;
+        typename E::Params ep{q16, D, D, 0, N_seq, nullptr, nullptr};
+        SATB_PROPAGATE((linear_auto<E, BF16>(d->tmaps, a16, D, Mc, D, W.w_q, D, ep, st)));
+      } else {
         typedef EpiStore16<BF16> E;
         typename E::Params ep{q16, D, nullptr, 0};
         SATB_PROPAGATE((linear_auto<E, BF16>(d->tmaps, a16, D, Mc, D, W.w_q, D, ep, st)));

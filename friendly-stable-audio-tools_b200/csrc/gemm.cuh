@@ -648,6 +648,69 @@ struct EpiQkvRope {
   }
 };
 
+// 16-bit store of whole 64-wide heads with the optional cosine-similarity normalisation of q / k
+// (attn_kwargs.qk_norm, models/transformer.py:433-436: F.normalize(., dim=-1), eps 1e-12) for columns
+// below norm_cols, followed by the partial rotary of EpiQkvRope for columns below rope_cols.  Used for the
+// fused QKV projection, the cross-attention q projection and the (step-invariant) k | v projection when
+// the model is built with qk_norm; the thread owns one head (64 accumulator columns) of one row.
+template <bool BF16>
+struct EpiHeadNorm16 {
+  static constexpr int kCols = 64;
+  static constexpr int kStageBytes = 0;
+  struct Params {
+    void* out;
+    int ld;
+    int norm_cols;         // columns >= this are stored as they are (v)
+    int rope_cols;         // 0: no rotary
+    int seq_len;
+    const float* cos_tab;  // [seq_len, 16]
+    const float* sin_tab;
+  };
+  __device__ static __forceinline__ void apply(const Params& p, const EpiCtx& c, const uint32_t (&r)[64]) {
+    if (!c.valid) return;
+    float inv = 1.f;
+    if (c.col0 < p.norm_cols) {
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) ss = fmaf(__uint_as_float(r[j]), __uint_as_float(r[j]), ss);
+      inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + static_cast<size_t>(c.row) * p.ld + c.col0);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * inv;
+    if (c.col0 < p.rope_cols && p.cos_tab) {
+      const int pos = c.row % p.seq_len;
+      const float4* ct = reinterpret_cast<const float4*>(p.cos_tab + pos * 16);
+      const float4* st = reinterpret_cast<const float4*>(p.sin_tab + pos * 16);
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 cs = __ldg(ct + j4), sn = __ldg(st + j4);
+        const float cc[4] = {cs.x, cs.y, cs.z, cs.w}, ss4[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j4 * 4 + u;
+          const float a = v[j], b = v[j + 16];
+          v[j] = a * cc[u] - b * ss4[u];
+          v[j + 16] = b * cc[u] + a * ss4[u];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      dst[j] = make_uint4(Op16<BF16>::pack(v[8 * j], v[8 * j + 1]), Op16<BF16>::pack(v[8 * j + 2], v[8 * j + 3]),
+                          Op16<BF16>::pack(v[8 * j + 4], v[8 * j + 5]), Op16<BF16>::pack(v[8 * j + 6], v[8 * j + 7]));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t* q = &r[32 + 8 * j];
+      dst[4 + j] = make_uint4(Op16<BF16>::pack(__uint_as_float(q[0]) * inv, __uint_as_float(q[1]) * inv),
+                              Op16<BF16>::pack(__uint_as_float(q[2]) * inv, __uint_as_float(q[3]) * inv),
+                              Op16<BF16>::pack(__uint_as_float(q[4]) * inv, __uint_as_float(q[5]) * inv),
+                              Op16<BF16>::pack(__uint_as_float(q[6]) * inv, __uint_as_float(q[7]) * inv));
+    }
+  }
+};
+
 // SwiGLU epilogue (models/transformer.py:232-235: value = first half, gate = second
 // half of the projection).  The weight rows are interleaved at load time so every
 // 64-column group holds 32 value columns followed by their 32 gate columns:

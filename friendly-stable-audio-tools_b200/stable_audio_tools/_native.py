@@ -23,7 +23,7 @@ class NativeError(RuntimeError):
 class SatbDitConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in (
         "io_channels", "embed_dim", "depth", "num_heads", "cond_token_dim", "global_cond_dim",
-        "project_cond_tokens", "project_global_cond", "global_cond_type", "patch_size", "operand_dtype")]
+        "project_cond_tokens", "project_global_cond", "global_cond_type", "patch_size", "operand_dtype", "qk_norm")]
 
 
 SATB_MAX_STAGES = 8

@@ -65,6 +65,7 @@ class DiffusionTransformer(nn.Module):
         self.transformer_type = transformer_type
         self.global_cond_type = global_cond_type
         self.operand_dtype = operand_dtype
+        self.qk_norm = bool(kwargs.get("attn_kwargs", {}).get("qk_norm", False))
 
         feat_dim = 256
         self.timestep_features = FourierFeatures(1, feat_dim)
@@ -127,7 +128,7 @@ class DiffusionTransformer(nn.Module):
                 cond_token_dim=self.cond_token_dim, global_cond_dim=self.global_cond_dim,
                 project_cond_tokens=int(self.project_cond_tokens), project_global_cond=int(self.project_global_cond),
                 global_cond_type=1 if self.global_cond_type == "adaLN" else 0, patch_size=1,
-                operand_dtype=1 if self.operand_dtype == "bf16" else 0)
+                operand_dtype=1 if self.operand_dtype == "bf16" else 0, qk_norm=int(self.qk_norm))
             h = ctypes.c_void_p()
             _native.check(lib.satb_dit_create(ctypes.byref(cfg), ctypes.byref(h)))
             self.__dict__["_h"] = h

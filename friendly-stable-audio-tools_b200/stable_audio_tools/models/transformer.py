@@ -84,9 +84,10 @@ class Attention(_FusedModule):
     def __init__(self, dim, dim_heads=64, dim_context=None, causal=False, zero_init_output=True, qk_norm=False,
                  natten_kernel_size=None):
         super().__init__()
-        if causal or qk_norm or natten_kernel_size:
-            raise NotImplementedError("causal / qk_norm / neighbourhood attention are outside the native hot path")
+        if causal or natten_kernel_size:
+            raise NotImplementedError("causal / neighbourhood attention are outside the native hot path")
         self.dim, self.dim_heads = dim, dim_heads
+        self.qk_norm = bool(qk_norm)      # cosine-similarity attention (reference transformer.py:433-436)
         dim_kv = dim_context if dim_context else dim
         self.num_heads = dim // dim_heads
         self.kv_heads = dim_kv // dim_heads

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define SATB_ABI_VERSION 1
+#define SATB_ABI_VERSION 2
 
 typedef struct SatbDit SatbDit;
 typedef struct SatbOobleck SatbOobleck;
@@ -39,6 +39,8 @@ typedef struct SatbDitConfig {
   int global_cond_type;     /* 0 = "prepend", 1 = "adaLN" (dit.py:29,185-204) */
   int patch_size;           /* must be 1 */
   int operand_dtype;        /* 0 = fp16 (the reference's autocast dtype), 1 = bf16 */
+  int qk_norm;              /* 1 = L2-normalise q and k per head before RoPE / attention
+                               (attn_kwargs.qk_norm, models/transformer.py:298,433-436) */
 } SatbDitConfig;
 
 /* Mirrors OobleckEncoder/OobleckDecoder kwargs (models/autoencoders.py:119-194). */

@@ -79,11 +79,14 @@ def _heads(x, h):
     return x.view(b, n, h, -1).permute(0, 2, 1, 3)
 
 
-def self_attention(x, sd, pfx, dim_heads, freqs):
-    """models/transformer.py:407-554, fused to_qkv branch (:430-431), RoPE (:438-452)."""
+def self_attention(x, sd, pfx, dim_heads, freqs, qk_norm=False):
+    """models/transformer.py:407-554, fused to_qkv branch (:430-431), optional cosine-sim
+    normalisation of q and k (:433-436), RoPE (:438-452)."""
     h = x.shape[-1] // dim_heads
     q, k, v = _lin(x, sd[pfx + "to_qkv.weight"]).chunk(3, dim=-1)
     q, k, v = (_heads(t, h) for t in (q, k, v))
+    if qk_norm:
+        q, k = F.normalize(q, dim=-1), F.normalize(k, dim=-1)
     if freqs is not None:
         # the reference forces q, k to fp32 here (:444-446); apply_rotary promotes
         # to at least fp32 itself, and the fp64 mode of this oracle keeps fp64.
@@ -94,7 +97,7 @@ def self_attention(x, sd, pfx, dim_heads, freqs):
     return _lin(o, sd[pfx + "to_out.weight"])
 
 
-def cross_attention(x, ctx, sd, pfx, dim_heads):
+def cross_attention(x, ctx, sd, pfx, dim_heads, qk_norm=False):
     """models/transformer.py:420-427 (separate to_q / to_kv), kv_heads =
     dim_context // dim_heads (:306-312); no RoPE when a context is given (:438)."""
     h = x.shape[-1] // dim_heads
@@ -102,6 +105,8 @@ def cross_attention(x, ctx, sd, pfx, dim_heads):
     k, v = _lin(ctx, sd[pfx + "to_kv.weight"]).chunk(2, dim=-1)
     kv_h = k.shape[-1] // dim_heads
     k, v = _heads(k, kv_h), _heads(v, kv_h)
+    if qk_norm:                                                                  # transformer.py:433-436
+        q, k = F.normalize(q, dim=-1), F.normalize(k, dim=-1)
     o = attention_core(q, k, v)
     o = o.permute(0, 2, 1, 3).reshape(x.shape[0], x.shape[1], -1)
     return _lin(o, sd[pfx + "to_out.weight"])
@@ -116,7 +121,7 @@ def feed_forward(x, sd, pfx):
     return _lin(m, sd[pfx + "ff.2.weight"], sd.get(pfx + "ff.2.bias"))
 
 
-def transformer_block(x, ctx, global_cond, sd, pfx, dim_heads, freqs):
+def transformer_block(x, ctx, global_cond, sd, pfx, dim_heads, freqs, qk_norm=False):
     """models/transformer.py:656-702."""
     ssg_key = pfx + "to_scale_shift_gate.1.weight"
     has_cross = (pfx + "cross_attn.to_q.weight") in sd and ctx is not None
@@ -127,11 +132,11 @@ def transformer_block(x, ctx, global_cond, sd, pfx, dim_heads, freqs):
         res = x
         a = layer_norm(x, sd[pfx + "pre_norm.gamma"], sd.get(pfx + "pre_norm.beta"))
         a = a * (1 + scale_self) + shift_self
-        a = self_attention(a, sd, pfx + "self_attn.", dim_heads, freqs)
+        a = self_attention(a, sd, pfx + "self_attn.", dim_heads, freqs, qk_norm)
         x = a * torch.sigmoid(1 - gate_self) + res
         if has_cross:
             a = layer_norm(x, sd[pfx + "cross_attend_norm.gamma"], sd.get(pfx + "cross_attend_norm.beta"))
-            x = x + cross_attention(a, ctx, sd, pfx + "cross_attn.", dim_heads)
+            x = x + cross_attention(a, ctx, sd, pfx + "cross_attn.", dim_heads, qk_norm)
         res = x
         a = layer_norm(x, sd[pfx + "ff_norm.gamma"], sd.get(pfx + "ff_norm.beta"))
         a = a * (1 + scale_ff) + shift_ff
@@ -140,16 +145,16 @@ def transformer_block(x, ctx, global_cond, sd, pfx, dim_heads, freqs):
     else:
         # plain branch, :691-700
         a = layer_norm(x, sd[pfx + "pre_norm.gamma"], sd.get(pfx + "pre_norm.beta"))
-        x = x + self_attention(a, sd, pfx + "self_attn.", dim_heads, freqs)
+        x = x + self_attention(a, sd, pfx + "self_attn.", dim_heads, freqs, qk_norm)
         if has_cross:
             a = layer_norm(x, sd[pfx + "cross_attend_norm.gamma"], sd.get(pfx + "cross_attend_norm.beta"))
-            x = x + cross_attention(a, ctx, sd, pfx + "cross_attn.", dim_heads)
+            x = x + cross_attention(a, ctx, sd, pfx + "cross_attn.", dim_heads, qk_norm)
         a = layer_norm(x, sd[pfx + "ff_norm.gamma"], sd.get(pfx + "ff_norm.beta"))
         x = x + feed_forward(a, sd, pfx + "ff.")
     return x
 
 
-def continuous_transformer(x, prepend, ctx, global_cond, sd, depth, dim_heads, hidden_states=None):
+def continuous_transformer(x, prepend, ctx, global_cond, sd, depth, dim_heads, hidden_states=None, qk_norm=False):
     """models/transformer.py:764-809: project_in, cat prepend, rotary table for
     the full length (prepend token = position 0), blocks, project_out."""
     pfx = "transformer."
@@ -160,7 +165,7 @@ def continuous_transformer(x, prepend, ctx, global_cond, sd, depth, dim_heads, h
     if (pfx + "rotary_pos_emb.inv_freq") in sd:
         freqs = rotary_freqs(x.shape[1], sd[pfx + "rotary_pos_emb.inv_freq"])
     for i in range(depth):
-        x = transformer_block(x, ctx, global_cond, sd, f"{pfx}layers.{i}.", dim_heads, freqs)
+        x = transformer_block(x, ctx, global_cond, sd, f"{pfx}layers.{i}.", dim_heads, freqs, qk_norm)
         if hidden_states is not None:
             hidden_states.append(x)
     return _lin(x, sd[pfx + "project_out.weight"])
@@ -196,7 +201,8 @@ def dit_inner_forward(sd, cfg, x, t, cross_attn_cond=None, global_embed=None, hi
         x = x.reshape(b, tp // patch, patch, c).transpose(2, 3).reshape(b, tp // patch, c * patch)
     out = continuous_transformer(x, prepend, cross_attn_cond,
                                  global_embed if gtype == "adaLN" else None,
-                                 sd, depth, dim_heads, hidden_states)
+                                 sd, depth, dim_heads, hidden_states,
+                                 qk_norm=bool(cfg.get("attn_kwargs", {}).get("qk_norm", False)))
     out = out.transpose(1, 2)[:, :, prepend_length:]                             # dit.py:219
     if patch > 1:                                                                # "b (c p) t -> b c (t p)"
         b, cp, tt = out.shape

@@ -41,12 +41,15 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
-def gen_dit(ref, gtype, path, patch_size=1):
+def gen_dit(ref, gtype, path, patch_size=1, qk_norm=False):
     cfg = dict(DIT_SMALL, global_cond_type=gtype)
     seed = 11 if gtype == "prepend" else 12
     if patch_size > 1:
         cfg["patch_size"] = patch_size
         seed = 13
+    if qk_norm:
+        cfg["attn_kwargs"] = {"qk_norm": True}
+        seed = 14
     sd = do.make_dit_weights(cfg, seed=seed)
     m = ref.dit.DiffusionTransformer(**cfg).eval()
     m.load_state_dict(sd, strict=True)
@@ -130,6 +133,7 @@ def main():
     gen_dit(ref, "prepend", os.path.join(GOLDEN_DIR, "dit_prepend_small.npz"))
     gen_dit(ref, "adaLN", os.path.join(GOLDEN_DIR, "dit_adaln_small.npz"))
     gen_dit(ref, "prepend", os.path.join(GOLDEN_DIR, "dit_patch2_small.npz"), patch_size=2)
+    gen_dit(ref, "prepend", os.path.join(GOLDEN_DIR, "dit_qknorm_small.npz"), qk_norm=True)
     gen_rope(ref, os.path.join(GOLDEN_DIR, "rope_1025.npz"))
     gen_snake(ref, os.path.join(GOLDEN_DIR, "snake_beta.npz"))
     gen_oobleck(ref, os.path.join(GOLDEN_DIR, "oobleck_small.npz"))

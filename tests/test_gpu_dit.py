@@ -33,7 +33,8 @@ def _golden_case(name):
     return g, cfg, sd
 
 
-@pytest.mark.parametrize("name", ["dit_prepend_small.npz", "dit_adaln_small.npz", "dit_patch2_small.npz"])
+@pytest.mark.parametrize("name", ["dit_prepend_small.npz", "dit_adaln_small.npz", "dit_patch2_small.npz",
+                                  "dit_qknorm_small.npz"])
 @pytest.mark.parametrize("dtype", ["fp16", "bf16"])
 def test_dit_small_vs_reference_golden(name, dtype):
     g, cfg, sd = _golden_case(name)
