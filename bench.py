@@ -265,40 +265,26 @@ def run_native(args):
     ones = torch.ones(BATCH, device=device)
     import math
 
+    from stable_audio_tools.inference.sampling import MultistepSdeStepper
+
     class Loop:
-        """dpmpp-3m-sde state machine, one model call per step (restated k-diffusion, see sampling.py)."""
+        """dpmpp-3m-sde, one model call per step: the product's own stepper (inference/sampling.py), which on CUDA
+        runs the VDenoiser scalings + the multistep update + the noise injection as one fused kernel."""
 
         def __init__(self):
-            self.x = x0.clone()
-            self.i = 0
-            self.d1 = self.d2 = None
-            self.h1 = self.h2 = None
+            self.st = MultistepSdeStepper(denoiser, x0.clone(), sigmas, order=3, extra_args=cond)
+            self.n = 0
+
+        @property
+        def x(self):
+            return self.st.x
 
         def step(self, x_in=None):
-            i = self.i % (GEN_STEPS - 1)      # stay inside the non-terminal part of the schedule
-            x = self.x if x_in is None else x_in
-            den = denoiser(x, sigmas[i] * ones, **cond)
-            h = math.log(sig[i]) - math.log(sig[i + 1])
-            h_eta = 2 * h
-            xn = math.exp(-h_eta) * x + (-math.expm1(-h_eta)) * den
-            if self.h2 is not None:
-                r0, r1 = self.h1 / h, self.h2 / h
-                d1_0 = (den - self.d1) / r0
-                d1_1 = (self.d1 - self.d2) / r1
-                d1 = d1_0 + (d1_0 - d1_1) * (r0 / (r0 + r1))
-                dd2 = (d1_0 - d1_1) / (r0 + r1)
-                phi_2 = math.expm1(-h_eta) / h_eta + 1
-                phi_3 = phi_2 / h_eta - 0.5
-                xn = xn + phi_2 * d1 - phi_3 * dd2
-            elif self.h1 is not None:
-                phi_2 = math.expm1(-h_eta) / h_eta + 1
-                xn = xn + phi_2 * ((den - self.d1) / (self.h1 / h))
-            xn = xn + torch.randn_like(x) * (sig[i + 1] * math.sqrt(-math.expm1(-2 * h)))
-            self.d1, self.d2 = den, self.d1
-            self.h1, self.h2 = h, self.h1
-            self.x = xn
-            self.i += 1
-            return xn
+            if x_in is not None:              # e2e: this step's latents arrive from the host
+                self.st.x, self.st.x_in = x_in, None
+            i = self.n % (GEN_STEPS - 1)      # stay inside the non-terminal part of the schedule
+            self.n += 1
+            return self.st.step(i)
 
     def barrier():
         if dist:
@@ -341,7 +327,7 @@ def run_native(args):
     out_host = torch.empty(BATCH, 64, LATENT_LEN, pin_memory=True)
     x_dev = torch.empty(BATCH, 64, LATENT_LEN, device=device)
     loop2 = Loop()
-    loop2.d1, loop2.d2, loop2.h1, loop2.h2, loop2.i = loop.d1, loop.d2, loop.h1, loop.h2, loop.i
+    loop2.st.den_1, loop2.st.den_2, loop2.st.h_1, loop2.st.h_2, loop2.n = loop.st.den_1, loop.st.den_2, loop.st.h_1, loop.st.h_2, loop.n
     for _ in range(max(args.warmup, 3)):
         x_dev.copy_(x_host, non_blocking=True)
         out_host.copy_(loop2.step(x_dev), non_blocking=True)

@@ -45,6 +45,14 @@ int satb_linear_f32out(const void* a16, const void* w16, float* c, int M, int N,
   return bf16 ? launch_gemm<EpiStore32, 64, true>(ta, tb, s, ep, st) : launch_gemm<EpiStore32, 64, false>(ta, tb, s, ep, st);
 }
 
+int satb_sampler_update(const float* x, const float* v, const float* den_1, const float* den_2, const float* noise,
+                        float* den, float* x_next, float* x_in_next, long long n, float c_skip, float c_out, float a,
+                        float b, float c, float d, float s, float c_in_next, void* stream) {
+  SATB_REQUIRE(x && v && den && x_next, "null argument");
+  return launch_sampler_update(x, v, den_1, den_2, noise, den, x_next, x_in_next, n, c_skip, c_out, a, b, c, d, s,
+                               c_in_next, static_cast<cudaStream_t>(stream));
+}
+
 int satb_attention(const void* q16, const void* k16, const void* v16, void* o16, int B, int H, int Hkv, int Nq, int Nk,
                    int bf16, void* stream) {
   SATB_REQUIRE(q16 && k16 && v16 && o16, "null argument");

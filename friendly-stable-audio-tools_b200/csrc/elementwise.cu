@@ -361,6 +361,61 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, void
   return 0;
 }
 
+// One sampler step of the v-objective k-diffusion samplers as a single pass (inference/sampling.py:
+// VDenoiser scalings + the DPM-Solver++ multistep update + noise injection are all linear in the tensors):
+//   den    = c_out * v + c_skip * x                      (VDenoiser.forward)
+//   x_next = A x + B den + C den_1 + D den_2 + S noise   (scalars from the host-side step-size algebra)
+//   x_in   = x_next * c_in_next                          (the next model call's input)
+// den_1 / den_2 / noise may be null (their coefficient is then ignored).
+__global__ void __launch_bounds__(256) sampler_update_kernel(const float4* __restrict__ x, const float4* __restrict__ v,
+                                                             const float4* __restrict__ d1, const float4* __restrict__ d2,
+                                                             const float4* __restrict__ nz, float4* __restrict__ den,
+                                                             float4* __restrict__ x_next, float4* __restrict__ x_in,
+                                                             long long n4, float c_skip, float c_out, float A, float B,
+                                                             float C, float D, float S, float c_in_next) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 xv = x[i], vv = v[i];
+    float4 dn = make_float4(fmaf(c_out, vv.x, c_skip * xv.x), fmaf(c_out, vv.y, c_skip * xv.y),
+                            fmaf(c_out, vv.z, c_skip * xv.z), fmaf(c_out, vv.w, c_skip * xv.w));
+    float4 o = make_float4(fmaf(A, xv.x, B * dn.x), fmaf(A, xv.y, B * dn.y), fmaf(A, xv.z, B * dn.z),
+                           fmaf(A, xv.w, B * dn.w));
+    if (d1) {
+      const float4 t = d1[i];
+      o.x = fmaf(C, t.x, o.x); o.y = fmaf(C, t.y, o.y); o.z = fmaf(C, t.z, o.z); o.w = fmaf(C, t.w, o.w);
+    }
+    if (d2) {
+      const float4 t = d2[i];
+      o.x = fmaf(D, t.x, o.x); o.y = fmaf(D, t.y, o.y); o.z = fmaf(D, t.z, o.z); o.w = fmaf(D, t.w, o.w);
+    }
+    if (nz) {
+      const float4 t = nz[i];
+      o.x = fmaf(S, t.x, o.x); o.y = fmaf(S, t.y, o.y); o.z = fmaf(S, t.z, o.z); o.w = fmaf(S, t.w, o.w);
+    }
+    den[i] = dn;
+    x_next[i] = o;
+    if (x_in) x_in[i] = make_float4(o.x * c_in_next, o.y * c_in_next, o.z * c_in_next, o.w * c_in_next);
+  }
+}
+
+int launch_sampler_update(const float* x, const float* v, const float* d1, const float* d2, const float* nz, float* den,
+                          float* x_next, float* x_in, long long n, float c_skip, float c_out, float A, float B, float C,
+                          float D, float S, float c_in_next, cudaStream_t stream) {
+  SATB_REQUIRE(n > 0 && n % 4 == 0, "sampler update: element count must be a positive multiple of 4");
+  const long long n4 = n / 4;
+  int grid = static_cast<int>(ceil_div64(n4, 256));
+  if (grid > 4 * device_sm_count()) grid = 4 * device_sm_count();
+  SATB_CHECK_CUDA(launch_pdl(sampler_update_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const float4*>(x),
+                             reinterpret_cast<const float4*>(v), reinterpret_cast<const float4*>(d1),
+                             reinterpret_cast<const float4*>(d2), reinterpret_cast<const float4*>(nz),
+                             reinterpret_cast<float4*>(den), reinterpret_cast<float4*>(x_next),
+                             reinterpret_cast<float4*>(x_in), n4, c_skip, c_out, A, B, C, D, S, c_in_next));
+  count_launch();
+  return 0;
+}
+
 int launch_snake_beta(const float* x, const float* alpha, const float* beta, float* y, int B, int C, int64_t T,
                       int logscale, cudaStream_t stream) {
   if (B <= 0 || C <= 0 || T <= 0) return 0;

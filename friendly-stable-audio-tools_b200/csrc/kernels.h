@@ -20,6 +20,10 @@ bool gemm_use_2cta();          // SATB_GEMM=1cta disables the CTA-pair GEMM (A/B
 int launch_layernorm(const float* x, const float* gamma, const float* beta, void* out16, int rows, int D,
                      const float* scale, const float* shift, int64_t mod_stride, int rows_per_item, int n_items,
                      bool bf16, cudaStream_t stream);
+// Fused VDenoiser scaling + multistep sampler update + noise (see elementwise.cu).
+int launch_sampler_update(const float* x, const float* v, const float* d1, const float* d2, const float* nz, float* den,
+                          float* x_next, float* x_in, long long n, float c_skip, float c_out, float A, float B, float C,
+                          float D, float S, float c_in_next, cudaStream_t stream);
 // SnakeBeta on [B, C, T] fp32 (log-scale alpha/beta per channel).
 int launch_snake_beta(const float* x, const float* alpha, const float* beta, float* y, int B, int C, int64_t T,
                       int logscale, cudaStream_t stream);

@@ -63,75 +63,124 @@ def _noise_fn(x, noise_sampler):
     return lambda sigma, sigma_next: torch.randn_like(x)
 
 
+class MultistepSdeStepper:
+    """DPM-Solver++(2M) SDE / DPM-Solver++(3M) SDE as a state machine with one model call per ``step()``.
+
+    Every update of both samplers is linear in the tensors involved,
+        x_next = A x + B den + C den_1 + D den_2 + S noise,
+    with scalars that depend only on the sigma schedule (``coeffs``).  On CUDA, with the standard ``VDenoiser``
+    wrapper and no callback, the denoiser scalings, this update and the scaling of the next model input run
+    as ONE kernel (``satb_sampler_update``) instead of ~20 elementwise launches; otherwise the same algebra is
+    evaluated with torch ops (CPU tensors in the tests, callbacks that need ``denoised`` before the update).
+    """
+
+    def __init__(self, model, x, sigmas, order=3, extra_args=None, callback=None, eta=1.0, s_noise=1.0,
+                 noise_sampler=None, solver_type="midpoint"):
+        self.model, self.x, self.sigmas, self.order = model, x, sigmas, order
+        self.extra_args, self.callback = extra_args or {}, callback
+        self.eta, self.s_noise, self.solver_type = eta, s_noise, solver_type
+        self.noise = _noise_fn(x, noise_sampler)
+        self.sig = [float(v) for v in sigmas]          # host copies: no device sync inside the loop
+        self.ones = x.new_ones([x.shape[0]])
+        self.i = 0
+        self.den_1 = self.den_2 = None
+        self.h_1 = self.h_2 = None
+        self.fused = (isinstance(model, VDenoiser) and callback is None and x.is_cuda and x.dtype == torch.float32
+                      and x.numel() % 4 == 0)
+        self.x_in = None                               # x * c_in(sigma_i), produced by the previous fused update
+
+    def coeffs(self, i):
+        """(A, B, C, D, S, h) of step i; C / D are 0 while the history is shorter than the order."""
+        sig, eta = self.sig, self.eta
+        if sig[i + 1] == 0:
+            return 0.0, 1.0, 0.0, 0.0, 0.0, None
+        h = math.log(sig[i]) - math.log(sig[i + 1])
+        C = D = 0.0
+        if self.order == 2:
+            eta_h = eta * h
+            A = sig[i + 1] / sig[i] * math.exp(-eta_h)
+            E = -math.expm1(-h - eta_h)
+            B = E
+            if self.den_1 is not None:
+                r = self.h_1 / h
+                K = (E / (-h - eta_h) + 1) / r if self.solver_type == "heun" else 0.5 * E / r
+                B, C = B + K, -K
+            S = sig[i + 1] * math.sqrt(-math.expm1(-2 * eta_h)) * self.s_noise if eta else 0.0
+        else:
+            h_eta = h * (eta + 1)
+            A = math.exp(-h_eta)
+            B = -math.expm1(-h_eta)
+            phi_2 = math.expm1(-h_eta) / h_eta + 1
+            if self.h_2 is not None:
+                r0, r1 = self.h_1 / h, self.h_2 / h
+                w, q = r0 / (r0 + r1), 1.0 / (r0 + r1)
+                phi_3 = phi_2 / h_eta - 0.5
+                P, Q = phi_2 * (1 + w) - phi_3 * q, -phi_2 * w + phi_3 * q
+                B, C, D = B + P / r0, -P / r0 + Q / r1, -Q / r1
+            elif self.h_1 is not None:
+                r = self.h_1 / h
+                B, C = B + phi_2 / r, -phi_2 / r
+            S = sig[i + 1] * math.sqrt(-math.expm1(-2 * h * eta)) * self.s_noise if eta else 0.0
+        return A, B, C, D, S, h
+
+    def step(self, i=None):
+        """One model evaluation + update at schedule index i (default: the next one); returns the new x."""
+        i = self.i if i is None else i
+        x, sig = self.x, self.sig
+        A, B, C, D, S, h = self.coeffs(i)
+        nz = self.noise(self.sigmas[i], self.sigmas[i + 1]) if S != 0.0 else None
+        if self.fused:
+            from .. import _native
+            c_skip, c_out, c_in = (float(c) for c in self.model.get_scalings(torch.tensor(sig[i], dtype=torch.float64)))
+            if self.x_in is None:
+                self.x_in = x * c_in
+            t = self.model.sigma_to_t(self.sigmas[i]) * self.ones
+            v = self.model.inner_model(self.x_in, t, **self.extra_args)
+            v = v.to(torch.float32).contiguous()
+            c_in_next = 1.0 / math.sqrt(sig[i + 1] ** 2 + self.model.sigma_data ** 2)
+            den, x_next, x_in_next = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+            xc = x.contiguous()
+            _native.check(_native.lib().satb_sampler_update(
+                _native.ptr(xc), _native.ptr(v), _native.ptr(self.den_1 if C != 0.0 else None),
+                _native.ptr(self.den_2 if D != 0.0 else None), _native.ptr(nz.contiguous() if nz is not None else None),
+                _native.ptr(den), _native.ptr(x_next), _native.ptr(x_in_next), x.numel(), c_skip, c_out, A, B, C, D, S,
+                c_in_next, _native.stream_ptr(x.device)))
+            self.x_in = x_in_next
+        else:
+            den = self.model(x, self.sigmas[i] * self.ones, **self.extra_args)
+            if self.callback is not None:
+                self.callback({"x": x, "i": i, "sigma": self.sigmas[i], "sigma_hat": self.sigmas[i], "denoised": den})
+            x_next = den if (A == 0.0 and B == 1.0) else A * x + B * den
+            if C != 0.0:
+                x_next = x_next + C * self.den_1
+            if D != 0.0:
+                x_next = x_next + D * self.den_2
+            if nz is not None:
+                x_next = x_next + S * nz
+        self.den_1, self.den_2 = den, self.den_1
+        self.h_1, self.h_2 = h, self.h_1
+        self.x = x_next
+        self.i = i + 1
+        return x_next
+
+    def run(self):
+        for _ in range(len(self.sig) - 1):
+            self.step()
+        return self.x
+
+
 @torch.no_grad()
 def sample_dpmpp_2m_sde(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1.0, s_noise=1.0,
                         noise_sampler=None, solver_type="midpoint"):
-    noise = _noise_fn(x, noise_sampler)
-    extra_args = extra_args or {}
-    ones = x.new_ones([x.shape[0]])
-    sig = [float(s) for s in sigmas]          # host copies: no device sync inside the loop
-    prev_den, prev_h = None, None
-    for i in range(len(sig) - 1):
-        den = model(x, sigmas[i] * ones, **extra_args)
-        if callback is not None:
-            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": den})
-        h = None
-        if sig[i + 1] == 0:
-            x = den
-        else:
-            h = math.log(sig[i]) - math.log(sig[i + 1])
-            eta_h = eta * h
-            x = sig[i + 1] / sig[i] * math.exp(-eta_h) * x + (-math.expm1(-h - eta_h)) * den
-            if prev_den is not None:
-                r = prev_h / h
-                if solver_type == "heun":
-                    x = x + ((-math.expm1(-h - eta_h)) / (-h - eta_h) + 1) * (1 / r) * (den - prev_den)
-                else:
-                    x = x + 0.5 * (-math.expm1(-h - eta_h)) * (1 / r) * (den - prev_den)
-            if eta:
-                x = x + noise(sigmas[i], sigmas[i + 1]) * (sig[i + 1] * math.sqrt(-math.expm1(-2 * eta_h)) * s_noise)
-        prev_den, prev_h = den, h
-    return x
+    """DPM-Solver++(2M) SDE (Lu et al. 2022; k-diffusion's sample_dpmpp_2m_sde, eta = 1, 'midpoint')."""
+    return MultistepSdeStepper(model, x, sigmas, 2, extra_args, callback, eta, s_noise, noise_sampler, solver_type).run()
 
 
 @torch.no_grad()
 def sample_dpmpp_3m_sde(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1.0, s_noise=1.0,
                         noise_sampler=None):
-    noise = _noise_fn(x, noise_sampler)
-    extra_args = extra_args or {}
-    ones = x.new_ones([x.shape[0]])
-    sig = [float(s) for s in sigmas]
-    den_1 = den_2 = None
-    h_1 = h_2 = None
-    for i in range(len(sig) - 1):
-        den = model(x, sigmas[i] * ones, **extra_args)
-        if callback is not None:
-            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": den})
-        h = None
-        if sig[i + 1] == 0:
-            x = den
-        else:
-            h = math.log(sig[i]) - math.log(sig[i + 1])
-            h_eta = h * (eta + 1)
-            x = math.exp(-h_eta) * x + (-math.expm1(-h_eta)) * den
-            if h_2 is not None:
-                r0, r1 = h_1 / h, h_2 / h
-                d1_0 = (den - den_1) / r0
-                d1_1 = (den_1 - den_2) / r1
-                d1 = d1_0 + (d1_0 - d1_1) * (r0 / (r0 + r1))
-                d2 = (d1_0 - d1_1) / (r0 + r1)
-                phi_2 = math.expm1(-h_eta) / h_eta + 1
-                phi_3 = phi_2 / h_eta - 0.5
-                x = x + phi_2 * d1 - phi_3 * d2
-            elif h_1 is not None:
-                r = h_1 / h
-                phi_2 = math.expm1(-h_eta) / h_eta + 1
-                x = x + phi_2 * ((den - den_1) / r)
-            if eta:
-                x = x + noise(sigmas[i], sigmas[i + 1]) * (sig[i + 1] * math.sqrt(-math.expm1(-2 * h * eta)) * s_noise)
-        den_1, den_2 = den, den_1
-        h_1, h_2 = h, h_1
-    return x
+    """DPM-Solver++(3M) SDE (k-diffusion's sample_dpmpp_3m_sde, eta = 1)."""
+    return MultistepSdeStepper(model, x, sigmas, 3, extra_args, callback, eta, s_noise, noise_sampler).run()
 
 
 def _to_d(x, sigma, denoised):

@@ -104,6 +104,14 @@ int satb_layernorm(const float* x, const float* gamma, const float* beta, void* 
 /* C[M, N] (fp32) = A[M, K] * W[N, K]^T, A and W 16-bit (fp16/bf16 bits) row-major: nn.Linear
  * without bias (F.linear call sites transformer.py:422-430,548). */
 int satb_linear_f32out(const void* a16, const void* w16, float* c, int M, int N, int K, int bf16, void* stream);
+/* One step of the v-objective k-diffusion samplers in a single pass over the latents (replaces the
+ * ~20 elementwise torch kernels of K.external.VDenoiser.forward + sample_dpmpp_{2m,3m}_sde's update,
+ * reference call sites inference/sampling.py:159,225-228): with v = model(x * c_in, t),
+ *   den = c_out v + c_skip x;  x_next = a x + b den + c den_1 + d den_2 + s noise;  x_in_next = x_next * c_in_next.
+ * den_1, den_2, noise, x_in_next may be NULL; all tensors fp32 with n elements (n % 4 == 0). */
+int satb_sampler_update(const float* x, const float* v, const float* den_1, const float* den_2, const float* noise,
+                        float* den, float* x_next, float* x_in_next, long long n, float c_skip, float c_out, float a,
+                        float b, float c, float d, float s, float c_in_next, void* stream);
 /* softmax(q k^T / sqrt(64)) v (transformer.py:496-536): q [B, Nq, H*64], k/v [B, Nk, Hkv*64],
  * out [B, Nq, H*64]; 16-bit, contiguous. */
 int satb_attention(const void* q16, const void* k16, const void* v16, void* o16, int B, int H, int Hkv, int Nq, int Nk,
