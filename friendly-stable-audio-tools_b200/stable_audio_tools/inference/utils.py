@@ -1,36 +1,37 @@
-"""Audio preparation helpers (reference ``inference/utils.py:7-39`` and ``PadCrop``,
-``data/modification.py:12-24`` semantics)."""
+"""Bring user audio into the shape the pipeline works on: [batch, channels, samples] at the model's
+sample rate, exactly target_length long (behaviour of the reference's ``inference/utils.py``
+``prepare_audio`` / ``set_audio_channels`` and of its deterministic ``PadCrop``)."""
 import torch
 
 
-def set_audio_channels(audio, target_channels):
+def pad_crop(signal: torch.Tensor, n_samples: int) -> torch.Tensor:
+    """[channels, samples] -> [channels, n_samples]: truncate on the right or zero-fill on the right."""
+    kept = signal[:, :n_samples]
+    if kept.shape[1] == n_samples:
+        return kept.clone()
+    return torch.nn.functional.pad(kept, (0, n_samples - kept.shape[1]))
+
+
+def set_audio_channels(audio: torch.Tensor, target_channels: int) -> torch.Tensor:
+    """[B, C, T] -> mono by averaging, stereo by duplicating a mono channel or dropping extra channels."""
+    have = audio.shape[1]
     if target_channels == 1:
-        return audio.mean(1, keepdim=True)
-    if target_channels == 2:
-        if audio.shape[1] == 1:
-            return audio.repeat(1, 2, 1)
-        if audio.shape[1] > 2:
-            return audio[:, :2, :]
+        return audio.mean(dim=1, keepdim=True)
+    if target_channels == 2 and have == 1:
+        return audio.expand(-1, 2, -1).contiguous()
+    if target_channels == 2 and have > 2:
+        return audio[:, :2]
     return audio
 
 
-def pad_crop(signal, n_samples):
-    """Deterministic PadCrop: keep the first n_samples, zero-pad on the right."""
-    n, s = signal.shape
-    out = signal.new_zeros([n, n_samples])
-    out[:, :min(s, n_samples)] = signal[:, :n_samples]
-    return out
-
-
 def prepare_audio(audio, in_sr, target_sr, target_length, target_channels, device):
-    assert target_channels in (1, 2)
-    audio = audio.to(device)
+    if target_channels not in (1, 2):
+        raise AssertionError("target_channels must be 1 (mono) or 2 (stereo)")
+    wav = audio.to(device)
     if in_sr != target_sr:
-        from torchaudio import transforms as T
-        audio = T.Resample(in_sr, target_sr).to(device)(audio)
-    audio = pad_crop(audio, target_length)
-    if audio.dim() == 1:
-        audio = audio[None, None]
-    elif audio.dim() == 2:
-        audio = audio[None]
-    return set_audio_channels(audio, target_channels)
+        from torchaudio.transforms import Resample
+        wav = Resample(in_sr, target_sr).to(device)(wav)
+    wav = pad_crop(wav, target_length)
+    while wav.dim() < 3:                      # [T] -> [1, 1, T], [C, T] -> [1, C, T]
+        wav = wav.unsqueeze(0)
+    return set_audio_channels(wav, target_channels)
