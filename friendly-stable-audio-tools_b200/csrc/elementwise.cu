@@ -30,12 +30,21 @@ __global__ void __launch_bounds__(128, NV <= 8 ? 8 : (NV <= 12 ? 7 : 5)) layerno
                                                         int rows, int D, const float* __restrict__ scale,
                                                         const float* __restrict__ shift, int64_t mod_stride,
                                                         int rows_per_item, int n_items) {
+  // gamma / beta never depend on the previous kernel: the block copies them to shared memory BEFORE the
+  // programmatic-dependency wait (it is launched while the producer GEMM is still draining), so that after
+  // the wait the critical path is only: row loads -> two warp reductions -> smem reads -> stores.
+  extern __shared__ float4 ln_gb[];   // [D / 4] gamma, then [D / 4] beta (if any)
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  const int nv = D >> 7;  // float4 per lane
   pdl_launch_dependents();
+  for (int i = threadIdx.x; i < (D >> 2); i += blockDim.x) {
+    ln_gb[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+    if (beta) ln_gb[(D >> 2) + i] = __ldg(reinterpret_cast<const float4*>(beta) + i);
+  }
+  __syncthreads();
   pdl_wait();
   if (row >= rows) return;
-  const int nv = D >> 7;  // float4 per lane
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
   float4 v[NV];
   float sum = 0.f;
@@ -56,8 +65,8 @@ __global__ void __launch_bounds__(128, NV <= 8 ? 8 : (NV <= 12 ? 7 : 5)) layerno
     }
   }
   const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(D) + 1e-5f);
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  const float4* b4 = beta ? reinterpret_cast<const float4*>(beta) : nullptr;
+  const float4* g4 = ln_gb;
+  const float4* b4 = beta ? ln_gb + (D >> 2) : nullptr;
   const float4* sc4 = nullptr;
   const float4* sh4 = nullptr;
   if (scale) {
@@ -70,14 +79,14 @@ __global__ void __launch_bounds__(128, NV <= 8 ? 8 : (NV <= 12 ? 7 : 5)) layerno
   for (int i = 0; i < NV; ++i) {
     if (i < nv) {
       const int idx = lane + 32 * i;
-      const float4 g = __ldg(g4 + idx);
+      const float4 g = g4[idx];
       float4 y;
       y.x = (v[i].x - mean) * rstd * g.x;
       y.y = (v[i].y - mean) * rstd * g.y;
       y.z = (v[i].z - mean) * rstd * g.z;
       y.w = (v[i].w - mean) * rstd * g.w;
       if (b4) {
-        const float4 b = __ldg(b4 + idx);
+        const float4 b = b4[idx];
         y.x += b.x; y.y += b.y; y.z += b.z; y.w += b.w;
       }
       if (sc4) {
@@ -345,8 +354,8 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, void
   const int items = n_items > 0 ? n_items : 1;
   const int nv = D >> 7;
   auto go = [&](auto kern) -> int {
-    SATB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(128), 0, stream, x, gamma, beta, static_cast<uint16_t*>(out16), rows,
-                               D, scale, shift, mod_stride, rows_per_item, items));
+    SATB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(128), static_cast<size_t>(D) * 8, stream, x, gamma, beta,
+                               static_cast<uint16_t*>(out16), rows, D, scale, shift, mod_stride, rows_per_item, items));
     return 0;
   };
   int rc;
