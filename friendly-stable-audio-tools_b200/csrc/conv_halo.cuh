@@ -88,15 +88,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
-  pdl_wait();
+  if (warp != 0) pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
       // ---------------------------------------------------------------- TMA producer
+      // the tap weights are static: their loads start before the programmatic-dependency wait
       mbar_expect_tx(b_full, Cfg::b_bytes(s));
       for (int t = 0; t < s.n_taps; ++t)
         for (int kb = 0; kb < kbs; ++kb)
           tma_load_2d(b_res + (t * kbs + kb) * Cfg::kBTile, &tmB, b_full, kb * kBlockK, t * s.cout);
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       const int tx = Cfg::halo_rows(s) * 128;

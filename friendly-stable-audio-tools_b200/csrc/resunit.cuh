@@ -130,7 +130,8 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
-  pdl_wait();
+  // Parameters and weights never depend on the previous kernel: they are fetched before the
+  // programmatic-dependency wait (per-channel parameters here, weight tiles by the producer below).
   if (threadIdx.x >= 128 && threadIdx.x < 128 + 3 * 32) {     // 96 threads x float4 = 3 x 128 floats
     const int i = threadIdx.x - 128;
     const float* src = i < 32 ? ep.bias7 : (i < 64 ? ep.sn2_a : ep.sn2_ib);
@@ -138,6 +139,7 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         src ? __ldg(reinterpret_cast<const float4*>(src) + (i & 31)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
+  if (warp != 0) pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -148,6 +150,19 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int a_tx = Cfg::halo_rows(s.dil) * 128;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
+      int b_pre = 0;   // conv7 weight tiles of the first tile issued before the dependency wait
+      if (cluster_id < total_tiles) {
+        for (; b_pre < Cfg::kStagesB && b_pre < Cfg::kKb * Cfg::kTaps; ++b_pre) {
+          const int kb = b_pre / Cfg::kTaps, tap = b_pre - kb * Cfg::kTaps;
+          if (rank == 0) mbar_expect_tx(&b_full[sb], 2 * Cfg::kTileB);
+          tma_load_2d_2sm(bs + sb * Cfg::kTileB, &tmB7, &b_full[sb], kb * kBlockK, tap * Cfg::kC + rank * (Cfg::kC / 2));
+          if (++sb == Cfg::kStagesB) {
+            sb = 0;
+            pb ^= 1;
+          }
+        }
+      }
+      pdl_wait();
       for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
         const int batch = tile / m_tiles;
         const int m0 = (tile - batch * m_tiles) * 2 * kBlockM + rank * kBlockM;
@@ -160,6 +175,7 @@ resunit_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
             pa ^= 1;
           }
           for (int tap = 0; tap < Cfg::kTaps; ++tap) {
+            if (tile == cluster_id && kb * Cfg::kTaps + tap < b_pre) continue;   // already in flight
             mbar_wait(&b_empty[sb], pb ^ 1);
             if (rank == 0) mbar_expect_tx(&b_full[sb], 2 * Cfg::kTileB);
             tma_load_2d_2sm(bs + sb * Cfg::kTileB, &tmB7, &b_full[sb], kb * kBlockK, tap * Cfg::kC + rank * (Cfg::kC / 2));
@@ -458,14 +474,14 @@ resunit256_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
-  pdl_wait();
-  if (threadIdx.x >= 128 && threadIdx.x < 128 + 3 * 64) {     // 192 threads x float4 = 3 x 256 floats
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + 3 * 64) {     // 192 threads x float4 = 3 x 256 floats (static: before the wait)
     const int i = threadIdx.x - 128;
     const float* src = i < 64 ? ep.bias7 : (i < 128 ? ep.sn2_a : ep.sn2_ib);
     reinterpret_cast<float4*>(prm)[i] =
         src ? __ldg(reinterpret_cast<const float4*>(src) + (i & 63)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
+  if (warp != 0) pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -482,6 +498,10 @@ resunit256_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __
           pb ^= 1;
         }
       };
+      int b_pre = 0;   // conv7 weight tiles of the first tile issued before the dependency wait
+      if (cluster_id < total_tiles)
+        for (; b_pre < Cfg::kStagesB; ++b_pre) load_b(&tmB7, 0, b_pre * Cfg::kC + rank * (Cfg::kC / 2));   // kb 0, taps 0..3
+      pdl_wait();
       for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
         const int batch = tile / m_tiles;
         const int m0 = (tile - batch * m_tiles) * 2 * kBlockM + rank * kBlockM;
@@ -493,7 +513,10 @@ resunit256_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __
             sa = 0;
             pa ^= 1;
           }
-          for (int tap = 0; tap < Cfg::kTaps; ++tap) load_b(&tmB7, kb * kBlockK, tap * Cfg::kC + rank * (Cfg::kC / 2));
+          for (int tap = 0; tap < Cfg::kTaps; ++tap) {
+            if (tile == cluster_id && kb * Cfg::kTaps + tap < b_pre) continue;   // already in flight
+            load_b(&tmB7, kb * kBlockK, tap * Cfg::kC + rank * (Cfg::kC / 2));
+          }
         }
         for (int kb = 0; kb < Cfg::kKb; ++kb) load_b(&tmB1, kb * kBlockK, rank * (Cfg::kC / 2));   // 1x1 weights
       }
