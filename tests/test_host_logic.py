@@ -184,8 +184,12 @@ sys.stdout.write('rank %d ok' % r + chr(10))   # one write per rank: the two ran
 sys.stdout.flush()
 """)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    import socket
+    with socket.socket() as sk:                     # a port that is free right now (no fixed port to collide on)
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                        capture_output=True, text=True, timeout=240, env=env)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "rank 0 ok" in p.stdout and "rank 1 ok" in p.stdout
