@@ -128,3 +128,24 @@ def test_fused_sampler_update_matches_the_torch_path(sampler_type):
     fn = so.sample_dpmpp_2m_sde if sampler_type == "dpmpp-2m-sde" else so.sample_dpmpp_3m_sde
     ref = fn(so.VDenoiser(model_fn), noise * sig[0], sig, extra_args={"gain": 0.7}, noise_sampler=sampler_for("cpu"))
     assert float((gpu - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_stream_decode_int16_matches_the_per_sample_path():
+    """stream_decode_int16 (decode of sample i+1 overlapped with the int16 conversion / D2H of sample i) yields
+    exactly what float_to_int16_audio gives sample by sample."""
+    from stable_audio_tools.utils.audio_utils import float_to_int16_audio, stream_decode_int16
+    torch.manual_seed(0)
+    w = torch.randn(2, 8, 3, device="cuda") * 0.4
+
+    def decode_fn(z):                       # stand-in decoder: [1, 8, L] -> [1, 2, 16 L]
+        y = torch.nn.functional.conv1d(z, w, padding=1)
+        return torch.repeat_interleave(y, 16, dim=2) * (1.0 + z.abs().mean())
+
+    lat = torch.randn(5, 8, 1000, device="cuda") * torch.tensor([0.1, 1.0, 3.0, 0.5, 2.0], device="cuda").view(5, 1, 1)
+    for maximize in (False, True):
+        got = [t.clone() for t in stream_decode_int16(decode_fn, lat, maximize=maximize)]
+        assert len(got) == 5
+        for i, g in enumerate(got):
+            ref = float_to_int16_audio(decode_fn(lat[i:i + 1])[0], maximize=maximize)
+            assert g.dtype == torch.int16 and g.shape == ref.shape
+            assert int((g.int() - ref.int()).abs().max()) <= 1, (i, maximize)   # at most one LSB
