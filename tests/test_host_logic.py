@@ -244,3 +244,33 @@ def test_rectified_flow_euler_sampler():
     init = torch.ones(2, 4, 16)
     out = sample_rf(model_fn, noise, init_data=init, steps=4, sigma_max=0.25, device="cpu", scale=0.0)
     assert torch.allclose(out, init * 0.75 + noise * 0.25, atol=1e-6)
+
+
+def test_unsupported_dit_inputs_fail_loudly_on_the_host():
+    """Options outside the built path raise before anything touches the GPU (no silent fallback)."""
+    from stable_audio_tools.models.dit import DiffusionTransformer
+    base = dict(io_channels=64, embed_dim=256, depth=1, num_heads=4, cond_token_dim=128, global_cond_dim=256,
+                project_cond_tokens=False)
+    with pytest.raises(NotImplementedError):
+        DiffusionTransformer(**base, transformer_type="x-transformers")
+    with pytest.raises(NotImplementedError):
+        DiffusionTransformer(**base, transformer_type="continuous_transformer", input_concat_dim=8)
+    with pytest.raises(NotImplementedError):
+        DiffusionTransformer(**base, transformer_type="continuous_transformer", prepend_cond_dim=8)
+    m = DiffusionTransformer(**base, transformer_type="continuous_transformer", patch_size=2,
+                             attn_kwargs={"qk_norm": True})
+    assert m.patch_size == 2 and m.qk_norm and m.transformer.layers[0].self_attn.qk_norm
+    assert m.transformer.project_in.weight.shape == (256, 128)          # io_channels * patch_size
+    x, t = torch.randn(1, 64, 32), torch.rand(1)
+    with pytest.raises(Exception) as ei:                                 # CPU tensors: no CPU path exists
+        m(x, t, cross_attn_cond=torch.randn(1, 4, 128), global_embed=torch.randn(1, 256))
+    assert "CUDA" in str(ei.value) or "cuda" in str(ei.value)
+
+
+def test_stream_decode_needs_cuda_latents():
+    from stable_audio_tools.utils.audio_utils import float_to_int16_audio, stream_decode_int16
+    with pytest.raises(RuntimeError):
+        next(stream_decode_int16(lambda z: z, torch.zeros(1, 2, 8)))
+    pcm = float_to_int16_audio(torch.tensor([[0.5, -2.0, 1.0]]))
+    assert pcm.dtype == torch.int16 and pcm.tolist() == [[8191, -32767, 16383]]    # peak 2 > 1 -> normalised
+    assert float_to_int16_audio(torch.tensor([[0.5, -0.25]]), maximize=True).tolist() == [[32767, -16383]]
