@@ -82,7 +82,21 @@ struct Op16<true> {
 extern unsigned long long g_launch_count;
 static inline void count_launch(int n = 1) { g_launch_count += n; }
 
-int device_sm_count();
+int device_sm_count();   // of the CURRENT device (cached per device)
+
+// "done once per device" flag for cudaFuncSetAttribute: function attributes are per device, and a process may
+// drive several devices (one handle each), so a process-wide static bool would skip the second device.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {   // true exactly once per current device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
 
 // Launch with programmatic stream serialization (PDL): the kernel must call pdl_wait() before its
 // first global-memory access.

@@ -208,11 +208,9 @@ int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvH
   const int smem = Cfg::stages(s) * Cfg::slot_bytes(s) + Cfg::b_bytes(s) + 256 + 1024;
   SATB_REQUIRE(s.K % kBlockK == 0 && s.cout <= Cfg::kBN && Cfg::halo_rows(s) <= 256 && Cfg::stages(s) >= 2,
                "conv_halo: unsupported shape");
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
+  SATB_REQUIRE(smem <= Cfg::kSmemBudget + 4096, "conv_halo: shared-memory request too large");
+  static PerDeviceOnce attr;   // once per device, to the largest size any shape may ask for
+  if (attr.first()) SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBudget + 4096));
   const int total = ceil_div(s.L, kBlockM) * s.batches;
   if (total <= 0) return 0;
   int grid = device_sm_count();

@@ -463,11 +463,8 @@ int launch_skinny_linear(const float* in, const float* W, const float* bias, con
   SATB_REQUIRE(K % 4 == 0, "skinny linear: K must be a multiple of 4");
   const size_t smem = static_cast<size_t>(8) * K * sizeof(float);
   SATB_REQUIRE(smem <= 200 * 1024, "skinny linear: K too large for the shared-memory row stage");
-  static size_t attr_smem = 48 * 1024;
-  if (smem > attr_smem) {
-    SATB_CHECK_CUDA(cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_smem = smem;
-  }
+  static PerDeviceOnce attr;
+  if (attr.first()) SATB_CHECK_CUDA(cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   skinny_linear_kernel<<<ceil_div(N, 8), 256, smem, stream>>>(in, W, bias, add, out, R, K, N, silu_out);
   count_launch();
   SATB_CHECK_CUDA(cudaGetLastError());

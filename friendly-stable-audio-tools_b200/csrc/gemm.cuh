@@ -937,11 +937,8 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape&
                 cudaStream_t stream) {
   using Cfg = GemmCfg<BN, Epi::kStageBytes>;
   auto kern = gemm_tcgen05_kernel<Epi, BN, BF16>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr;
+  if (attr.first()) SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const int m_tiles = ceil_div(s.L, kBlockM), n_tiles = ceil_div(s.N, BN);
   const int total = m_tiles * s.batches * n_tiles;
   if (total <= 0) return 0;
@@ -957,11 +954,8 @@ int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmS
                      cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN, Epi::kStageBytes>;
   auto kern = gemm_tcgen05_2cta_kernel<Epi, BN, BF16>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr;
+  if (attr.first()) SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const int m_tiles = ceil_div(s.L, 2 * kBlockM), n_tiles = ceil_div(s.N, BN);
   const int total = m_tiles * s.batches * n_tiles;
   if (total <= 0) return 0;

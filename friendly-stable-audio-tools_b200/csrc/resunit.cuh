@@ -367,11 +367,8 @@ int launch_resunit(const CUtensorMap& tmA, const CUtensorMap& tmB7, const CUtens
   using Cfg = ResUnitCfg;
   SATB_REQUIRE(s.dil >= 1 && s.dil <= Cfg::kMaxDil, "resunit: dilation out of range");
   auto kern = resunit_tcgen05_2cta_kernel<BF16>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr;
+  if (attr.first()) SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const int total = ceil_div(s.L, 2 * kBlockM) * s.batches;
   if (total <= 0) return 0;
   int clusters = device_sm_count() / 2;
@@ -702,11 +699,8 @@ int launch_resunit256(const CUtensorMap& tmA, const CUtensorMap& tmB7, const CUt
   using Cfg = ResUnit256Cfg;
   SATB_REQUIRE(s.dil >= 1 && s.dil <= Cfg::kMaxDil, "resunit256: dilation out of range");
   auto kern = resunit256_tcgen05_2cta_kernel<BF16>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr;
+  if (attr.first()) SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const int total = ceil_div(s.L, 2 * kBlockM) * s.batches;
   if (total <= 0) return 0;
   int clusters = device_sm_count() / 2;

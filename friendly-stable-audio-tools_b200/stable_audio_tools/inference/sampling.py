@@ -380,10 +380,11 @@ class _DPMSolver:
         h = abs(h_init) * (1 if forward else -1)
         b1, b2, b3 = (pcoeff + icoeff + dcoeff) / order, -(pcoeff + 2 * dcoeff) / order, dcoeff / order
         errs = None
-        s, x_prev, i = t_start, x, 0
+        s, x_prev, n_steps = t_start, x, 0
         while (s < t_end - 1e-5) if forward else (s > t_end + 1e-5):
             t = min(t_end, s + h) if forward else max(t_end, s + h)
             eps, cache = self.eps({}, "eps", x, s)
+            denoised = x - self.sigma(s) * eps          # reported below: the estimate at the OLD (x, s)
             if order == 2:
                 x_low, cache = self.step1(x, s, t, cache=cache)
                 x_high, cache = self.step2(x, s, t, cache=cache)
@@ -402,9 +403,14 @@ class _DPMSolver:
             if accept:
                 errs[2], errs[1] = errs[1], errs[0]
                 x_prev, x, s = x_low, x_high, t
-                self._report(x, i, s, cache)
-                i += 1
             h *= factor
+            n_steps += 1
+            # k-diffusion's contract (the inpainting callback relies on it): the callback fires on EVERY iteration,
+            # accepted or rejected, with i = the iteration count, x = the state after this iteration and sigma at
+            # the proposed t
+            if self.callback is not None:
+                sig = x.new_tensor(self.sigma(t))
+                self.callback({"x": x, "i": n_steps - 1, "t": t, "sigma": sig, "sigma_hat": sig, "denoised": denoised})
         return x
 
 

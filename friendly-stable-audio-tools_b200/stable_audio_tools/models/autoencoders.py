@@ -101,14 +101,12 @@ class _NativeOobleck(nn.Module):
         self.__dict__["_ncfg"] = dict(audio_channels=audio_channels, channels=channels, latent_dim=latent_dim,
                                       c_mults=list(c_mults), strides=list(strides), final_tanh=bool(final_tanh),
                                       operand_dtype=operand_dtype)
+        # also fires when a parent module's load_state_dict recurses into this one (see models/dit.py)
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.refresh_native_weights())
 
     def _apply(self, fn, *a, **k):
         self.__dict__["_dirty"] = True
         return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self.__dict__["_dirty"] = True
-        return super().load_state_dict(*a, **k)
 
     def refresh_native_weights(self):
         self.__dict__["_dirty"] = True
@@ -176,12 +174,13 @@ class OobleckEncoder(_NativeOobleck):
         """audio [B, in_channels, T] -> pre-bottleneck [B, latent_dim, T / prod(strides)]"""
         if not x.is_cuda:
             raise _native.NativeError("OobleckEncoder.forward needs CUDA tensors (no CPU fallback)")
-        h = self._handle(x.device)
-        xin = x.detach().to(torch.float32).contiguous()
-        B, C, T = xin.shape
-        out = torch.empty(B, self.latent_dim, T // self.downsampling_ratio, device=x.device, dtype=torch.float32)
-        _native.check(_native.lib().satb_oobleck_encode(h, _native.ptr(xin), _native.ptr(out), B, ctypes.c_longlong(T),
-                                                        _native.stream_ptr(x.device)))
+        with torch.cuda.device(x.device):            # the native handle / workspaces live on the model's device
+            h = self._handle(x.device)
+            xin = x.detach().to(torch.float32).contiguous()
+            B, C, T = xin.shape
+            out = torch.empty(B, self.latent_dim, T // self.downsampling_ratio, device=x.device, dtype=torch.float32)
+            _native.check(_native.lib().satb_oobleck_encode(h, _native.ptr(xin), _native.ptr(out), B,
+                                                            ctypes.c_longlong(T), _native.stream_ptr(x.device)))
         return out.to(x.dtype)
 
 
@@ -214,12 +213,13 @@ class OobleckDecoder(_NativeOobleck):
         """latents [B, latent_dim, L] -> audio [B, out_channels, L * prod(strides)]"""
         if not z.is_cuda:
             raise _native.NativeError("OobleckDecoder.forward needs CUDA tensors (no CPU fallback)")
-        h = self._handle(z.device)
-        zin = z.detach().to(torch.float32).contiguous()
-        B, C, L = zin.shape
-        out = torch.empty(B, self.out_channels, L * self.upsampling_ratio, device=z.device, dtype=torch.float32)
-        _native.check(_native.lib().satb_oobleck_decode(h, _native.ptr(zin), _native.ptr(out), B, L,
-                                                        _native.stream_ptr(z.device)))
+        with torch.cuda.device(z.device):            # the native handle / workspaces live on the model's device
+            h = self._handle(z.device)
+            zin = z.detach().to(torch.float32).contiguous()
+            B, C, L = zin.shape
+            out = torch.empty(B, self.out_channels, L * self.upsampling_ratio, device=z.device, dtype=torch.float32)
+            _native.check(_native.lib().satb_oobleck_decode(h, _native.ptr(zin), _native.ptr(out), B, L,
+                                                            _native.stream_ptr(z.device)))
         return out.to(z.dtype)
 
 

@@ -94,15 +94,17 @@ class DiffusionTransformer(nn.Module):
         self.__dict__["_weights_dirty"] = True
         self.__dict__["_cond_key"] = None
         self.__dict__["_keepalive"] = None
+        self.__dict__["_neg_masked"] = None
+        # nn.Module.load_state_dict on a PARENT (ConditionedDiffusionModelWrapper, DiTWrapper, copy_state_dict(model, sd))
+        # recurses through _load_from_state_dict and never calls a child's load_state_dict override; the post hook
+        # below is run for every module of the recursion, so the native copy is refreshed whichever way the
+        # parameters were (re)loaded.
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.refresh_native_weights())
 
     # ------------------------------------------------------------------ native plumbing
     def _apply(self, fn, *a, **k):
         self.__dict__["_weights_dirty"] = True
         return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self.__dict__["_weights_dirty"] = True
-        return super().load_state_dict(*a, **k)
 
     def refresh_native_weights(self):
         """Call after mutating parameters in place (``load_state_dict`` / ``.to()`` do it for you)."""
@@ -195,14 +197,18 @@ class DiffusionTransformer(nn.Module):
         if use_cfg and negative_cross_attn_cond is not None:
             neg = negative_cross_attn_cond
             if negative_cross_attn_mask is not None:
-                neg = torch.where(negative_cross_attn_mask.to(torch.bool).unsqueeze(2), neg, torch.zeros_like(neg))
-                # a fresh tensor every call would defeat the conditioning cache: reuse by content key
+                # masked once per (cond, mask) pair: the cache holds the raw tensors themselves (identity and
+                # version are compared, never a recycled data_ptr), so a later call with another negative prompt
+                # that the allocator placed at the same address cannot hit it
                 prev = self.__dict__.get("_neg_masked")
-                if prev is not None and prev[0] == (self._tkey(negative_cross_attn_cond), self._tkey(negative_cross_attn_mask)):
-                    neg = prev[1]
+                if (prev is not None and prev[0] is negative_cross_attn_cond and prev[1] is negative_cross_attn_mask
+                        and prev[2] == (negative_cross_attn_cond._version, negative_cross_attn_mask._version)):
+                    neg = prev[3]
                 else:
-                    self.__dict__["_neg_masked"] = ((self._tkey(negative_cross_attn_cond),
-                                                     self._tkey(negative_cross_attn_mask)), neg)
+                    neg = torch.where(negative_cross_attn_mask.to(torch.bool).unsqueeze(2), neg, torch.zeros_like(neg))
+                    self.__dict__["_neg_masked"] = (negative_cross_attn_cond, negative_cross_attn_mask,
+                                                    (negative_cross_attn_cond._version,
+                                                     negative_cross_attn_mask._version), neg)
         p = self.patch_size
         if p > 1:
             if x.shape[2] % p != 0:
@@ -220,25 +226,28 @@ class DiffusionTransformer(nn.Module):
                 return (out, {"hidden_states": []}) if return_info else out
             b_, c_, l_ = x.shape
             x = x.reshape(b_, c_, l_ // p, p).transpose(2, 3).reshape(b_, c_ * p, l_ // p)   # channel = c * p + pi
-        h = self._handle(x.device)
-        B, C, L = x.shape
-        self._prepare(h, cross_attn_cond, neg, global_embed, use_cfg, x.device, B)
-        xin = x.detach().to(torch.float32).contiguous()
-        tin = t.detach().to(torch.float32).contiguous()
-        out = torch.empty_like(xin)
-        st = _native.stream_ptr(x.device)
-        if return_info:
-            P = 0 if self.global_cond_type == "adaLN" else 1
-            rows = (2 * B if use_cfg else B) * (L + P)
-            hidden = torch.empty(rows, self.embed_dim, device=x.device, dtype=torch.float32)
-            _native.check(_native.lib().satb_dit_forward_debug(h, _native.ptr(xin), _native.ptr(tin), _native.ptr(out),
-                                                               _native.ptr(hidden), B, L, float(cfg_scale),
-                                                               float(scale_phi), st))
-            info = {"hidden_states": [hidden.view(-1, L + P, self.embed_dim)]}
-            return self._unpatch(out).to(x.dtype), info
-        _native.check(_native.lib().satb_dit_forward(h, _native.ptr(xin), _native.ptr(tin), _native.ptr(out), B, L,
-                                                     float(cfg_scale), float(scale_phi), st))
-        return self._unpatch(out).to(x.dtype)
+        # handles, workspaces and TMA descriptors live on the model's device: make it current for the native calls
+        # (generate_diffusion_cond(device='cuda:1') with current device 0 must work)
+        with torch.cuda.device(x.device):
+            h = self._handle(x.device)
+            B, C, L = x.shape
+            self._prepare(h, cross_attn_cond, neg, global_embed, use_cfg, x.device, B)
+            xin = x.detach().to(torch.float32).contiguous()
+            tin = t.detach().to(torch.float32).contiguous()
+            out = torch.empty_like(xin)
+            st = _native.stream_ptr(x.device)
+            if return_info:
+                P = 0 if self.global_cond_type == "adaLN" else 1
+                rows = (2 * B if use_cfg else B) * (L + P)
+                hidden = torch.empty(rows, self.embed_dim, device=x.device, dtype=torch.float32)
+                _native.check(_native.lib().satb_dit_forward_debug(h, _native.ptr(xin), _native.ptr(tin), _native.ptr(out),
+                                                                   _native.ptr(hidden), B, L, float(cfg_scale),
+                                                                   float(scale_phi), st))
+                info = {"hidden_states": [hidden.view(-1, L + P, self.embed_dim)]}
+                return self._unpatch(out).to(x.dtype), info
+            _native.check(_native.lib().satb_dit_forward(h, _native.ptr(xin), _native.ptr(tin), _native.ptr(out), B, L,
+                                                         float(cfg_scale), float(scale_phi), st))
+            return self._unpatch(out).to(x.dtype)
 
     def _unpatch(self, out):
         p = self.patch_size

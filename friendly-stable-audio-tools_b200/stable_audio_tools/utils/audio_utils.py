@@ -21,21 +21,24 @@ def stream_decode_int16(decode_fn, latents: torch.Tensor, maximize: bool = False
 
     ``decode_fn(z[1, C, L]) -> audio[1, channels, T]`` is e.g. ``model.pretransform.decode``.  Every sample is
     normalised on its own (like calling ``float_to_int16_audio`` per file, ``generate.py:142-151`` of the
-    reference).  The host buffers are pinned and reused, so a yielded tensor is only valid until the generator
-    is advanced twice more; copy it (or write the file) before that.
+    reference).  Three pinned host buffers are reused in rotation: sample k is handed out while sample k + 1 is in
+    flight; the next advance (which hands out k + 1) enqueues sample k + 2 into another buffer, and only the advance
+    after that reuses sample k's buffer.  So a yielded tensor stays valid across ONE further advance of the
+    generator (a one-deep writer queue is safe) and must be consumed or copied before the second.
     """
     if not latents.is_cuda:
         raise RuntimeError("stream_decode_int16 needs CUDA latents (the decoder has no CPU path)")
     main = torch.cuda.current_stream(latents.device)
     side = torch.cuda.Stream(device=latents.device)
-    pinned, done, pending = [None, None], [None, None], None
+    n_slots = 3
+    pinned, done, pending = [None] * n_slots, [None] * n_slots, None
     for i in range(latents.shape[0]):
         audio = decode_fn(latents[i:i + 1])[0]
         ready = torch.cuda.Event()
         ready.record(main)
-        slot = i & 1
+        slot = i % n_slots
         if done[slot] is not None:
-            done[slot].synchronize()                    # the consumer had two steps to finish with this buffer
+            done[slot].synchronize()                    # copy of sample i - 3; the consumer has had one full advance since it was handed out
         with torch.cuda.stream(side):
             side.wait_event(ready)
             peak = audio.abs().max()

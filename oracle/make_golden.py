@@ -127,6 +127,74 @@ def gen_oobleck(ref, path):
                         dec_chunked=_np(dec_chunked))
 
 
+# BASELINE.json configs[0]: Oobleck VAE reconstruct, 1 s mono 16 kHz white noise, the full SA-Open / SA-2.0 VAE
+# (autoencoders/stable_audio_2_0_vae.json with audio_channels / in_channels / out_channels / io_channels = 1,
+# sample_rate 16000), reconstruct_audio(chunked=True, chunk_size=7, overlap=1,
+# max_batch_size=20) as reconstruct_audios.py calls it for 1 s frames.
+MONO_ENC = dict(in_channels=1, channels=128, c_mults=[1, 2, 4, 8, 16], strides=[2, 4, 4, 8, 8], latent_dim=128,
+                use_snake=True)
+MONO_DEC = dict(out_channels=1, channels=128, c_mults=[1, 2, 4, 8, 16], strides=[2, 4, 4, 8, 8], latent_dim=64,
+                use_snake=True, final_tanh=False)
+
+
+class seeded_randn_like:
+    """Replaces torch.randn_like (the VAE draw, reference models/bottleneck.py:50) by draws from a seeded CPU
+    generator, so that the reference run here and the native run on the GPU box see the same noise."""
+
+    def __init__(self, seed):
+        self.gen = torch.Generator().manual_seed(seed)
+
+    def __call__(self, t, **kw):
+        return torch.randn(t.shape, generator=self.gen, dtype=torch.float32).to(device=t.device, dtype=t.dtype)
+
+    def __enter__(self):
+        self.prev = torch.randn_like
+        torch.randn_like = self
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn_like = self.prev
+
+
+class cpu_stream_randn_like:
+    """Replaces torch.randn_like by draws from the DEFAULT CPU generator (moved to the tensor's device): after
+    torch.manual_seed(s) a CUDA run sees the numbers the CPU reference drew when gen_oobleck made its golden."""
+
+    def __call__(self, t, **kw):
+        return torch.randn(t.shape, dtype=torch.float32).to(device=t.device, dtype=t.dtype)
+
+    def __enter__(self):
+        self.prev = torch.randn_like
+        torch.randn_like = self
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn_like = self.prev
+
+
+def gen_config1(ref, path):
+    esd = oo.make_oobleck_weights(oo.encoder_param_shapes(MONO_ENC), seed=31)
+    dsd = oo.make_oobleck_weights(oo.decoder_param_shapes(MONO_DEC), seed=32,
+                                  transposed=oo.decoder_transposed_prefixes(MONO_DEC))
+    cfg = {"model_type": "autoencoder", "sample_size": 65536, "sample_rate": 16000, "audio_channels": 1,
+           "model": {"encoder": {"type": "oobleck", "config": MONO_ENC}, "decoder": {"type": "oobleck", "config": MONO_DEC},
+                     "bottleneck": {"type": "vae"}, "latent_dim": 64, "downsampling_ratio": 2048, "io_channels": 1}}
+    # = create_autoencoder_from_config(cfg) (autoencoders.py:737-787); built directly because the factory's lazy
+    # relative imports need the reference registered in sys.modules, which ref_shims deliberately avoids
+    enc = ref.autoencoders.OobleckEncoder(**MONO_ENC)
+    dec = ref.autoencoders.OobleckDecoder(**MONO_DEC)
+    ae = ref.autoencoders.AudioAutoencoder(enc, dec, latent_dim=64, downsampling_ratio=2048, sample_rate=16000,
+                                           io_channels=1, bottleneck=ref.bottleneck.VAEBottleneck()).eval()
+    ae.encoder.load_state_dict(esd, strict=True)
+    ae.decoder.load_state_dict(dsd, strict=True)
+    g = torch.Generator().manual_seed(33)
+    audio = 0.5 * torch.randn(1, 1, 16000, generator=g).clamp(-1, 1)      # SURVEY.md 8(d) config 1
+    with torch.no_grad(), seeded_randn_like(34):
+        rec = ae.reconstruct_audio(audio.clone(), chunked=True, chunk_size=7, overlap=1, max_batch_size=20)
+    np.savez_compressed(path, model_cfg=json.dumps(cfg), enc_seed=31, dec_seed=32, noise_seed=34,
+                        enc_wsum=weights_checksum(esd), dec_wsum=weights_checksum(dsd), audio=_np(audio), rec=_np(rec))
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     ref = ref_shims.import_reference()
@@ -137,6 +205,7 @@ def main():
     gen_rope(ref, os.path.join(GOLDEN_DIR, "rope_1025.npz"))
     gen_snake(ref, os.path.join(GOLDEN_DIR, "snake_beta.npz"))
     gen_oobleck(ref, os.path.join(GOLDEN_DIR, "oobleck_small.npz"))
+    gen_config1(ref, os.path.join(GOLDEN_DIR, "config1_mono16k.npz"))
     for f in sorted(os.listdir(GOLDEN_DIR)):
         print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)))
 

@@ -130,6 +130,42 @@ def vae_encode(h, noise):
     return vae_sample(mean, scale, noise)
 
 
+def reconstruct_audio_chunked(audio, esd, dsd, ecfg, dcfg, chunk_size, overlap, max_batch_size, noise_fn):
+    """models/autoencoders.py:573-645 (AudioAutoencoder.reconstruct_audio, chunked=True) over the
+    restated encoder / VAE bottleneck / decoder: zero-pad to n_chunk + 1 hops (:605-607), cut chunks of
+    chunk_size latents hopping chunk_size - overlap (:609-616), encode -> vae_sample -> decode per batch of
+    max_batch_size chunks (:619-625), Bartlett cross-fade on the shared edges (:631-640), crop (:643).
+    noise_fn(mean) stands for the randn_like draw of bottleneck.py:50 (one call per encode batch)."""
+    bs, n_ch, sample_length = audio.shape
+    ratio = math.prod(ecfg["strides"])
+    overlap_s = overlap * ratio
+    win = torch.bartlett_window(overlap_s * 2)
+    chunk_s = chunk_size * ratio
+    hop = chunk_s - overlap_s
+    n_chunk = int(math.ceil((sample_length - chunk_s) / hop)) + 1
+    pad_len = chunk_s + hop * n_chunk - sample_length
+    audio = F.pad(audio, (0, pad_len))
+    chunks = torch.stack([audio[..., i * hop:i * hop + chunk_s] for i in range(n_chunk)], dim=1)
+    chunks = chunks.reshape(bs * n_chunk, n_ch, chunk_s)
+    xs = []
+    for head in range(0, chunks.shape[0], max_batch_size):
+        h = oobleck_encoder(chunks[head:head + max_batch_size], esd, ecfg)
+        mean, scale = h.chunk(2, dim=1)
+        z = vae_sample(mean, scale, noise_fn(mean))
+        xs.append(oobleck_decoder(z, dsd, dcfg))
+    xs = torch.cat(xs, dim=0)
+    xs = xs.reshape(bs, n_chunk, xs.shape[1], xs.shape[2])
+    rec = torch.zeros(bs, xs.shape[2], audio.shape[-1])
+    for i in range(n_chunk):
+        x_ = xs[:, i].clone()
+        if i != 0:
+            x_[:, :, :overlap_s] *= win[None, None, :overlap_s]
+        if i != n_chunk - 1:
+            x_[:, :, -overlap_s:] *= win[None, None, -overlap_s:]
+        rec[:, :, i * hop:i * hop + chunk_s] += x_
+    return rec[..., :sample_length]
+
+
 # ---------------------------------------------------------------------------
 # synthetic weights
 # ---------------------------------------------------------------------------

@@ -155,3 +155,65 @@ def sample_dpmpp_3m_sde(model, x, sigmas, extra_args=None, callback=None, disabl
         den_1, den_2 = den, den_1
         h_1, h_2 = h, h_1
     return x
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's own sampler front end and inpainting mask (these ARE under /root/reference and are pinned
+# against the live reference by tests/test_oracle_vs_reference.py).
+# ---------------------------------------------------------------------------------------------
+def get_bmask(i, steps, mask):
+    """inference/sampling.py:120-124: hard mask that shrinks as the step index grows."""
+    return torch.where(mask <= (i + 1) / steps, 1, 0)
+
+
+def build_mask(sample_size, mask_args):
+    """inference/generation.py:270-292: soft keep-mask over the latent positions (1 = keep the init audio),
+    Hann ramps of softnessL / softnessR percent on the two edges, scaled down by `marination`."""
+    pct = lambda key: mask_args[key] / 100.0 * sample_size
+    start, end = math.floor(pct("maskstart")), math.ceil(pct("maskend"))
+    n_l, n_r = round(pct("softnessL")), round(pct("softnessR"))
+    m = torch.zeros(sample_size)
+    m[start:end] = 1
+    m[start:start + n_l] = torch.hann_window(2 * n_l, periodic=False)[:n_l]
+    m[end - n_r:end] = torch.hann_window(2 * n_r, periodic=False)[n_r:]
+    if mask_args["marination"] > 0:
+        m = m * (1 - mask_args["marination"])
+    return m
+
+
+def cut_paste(init, sample_size, mask_args):
+    """inference/generation.py:197-210: move init[crop_from : crop_from + n] to paste_from (zeros elsewhere)."""
+    crop_from = math.floor(mask_args["cropfrom"] / 100.0 * sample_size)
+    paste_from = math.floor(mask_args["pastefrom"] / 100.0 * sample_size)
+    paste_to = math.ceil(mask_args["pasteto"] / 100.0 * sample_size)
+    n = min(paste_to - paste_from, sample_size - crop_from)
+    out = init.new_zeros(init.shape)
+    out[:, :, paste_from:paste_from + n] = init[:, :, crop_from:crop_from + n]
+    return out
+
+
+@torch.no_grad()
+def sample_k(model_fn, noise, init_data=None, mask=None, steps=100, sampler_type="dpmpp-2m-sde", sigma_min=0.5,
+             sigma_max=50, rho=1.0, noise_sampler=None, **extra_args):
+    """inference/sampling.py:144-228 for the two multistep SDE samplers: sigma schedule (:165), initial noise
+    scaled by sigma_0 (:167), variation start (:171-174), inpainting start + per-step callback that re-noises the
+    kept region with this step's sigma and the shrinking hard mask (:175-199), plain sampling (:203-206).
+    `noise_sampler` (not a reference argument) injects the SDE noise; None = randn_like like k-diffusion's default."""
+    den = VDenoiser(model_fn)
+    sigmas = get_sigmas_polyexponential(steps, sigma_min, sigma_max, rho)
+    noise = noise * sigmas[0]
+    callback = None
+    if init_data is not None and mask is None:
+        x = init_data + noise
+    elif init_data is not None:
+        b0 = get_bmask(0, steps, mask)
+        x = (init_data + noise) * b0 + noise * (1 - b0)
+
+        def callback(args):
+            renoised = init_data + torch.randn_like(init_data) * args["sigma"]
+            b = get_bmask(args["i"], steps, mask)
+            args["x"][:, :, :] = renoised * b + args["x"] * (1 - b)
+    else:
+        x = noise
+    fn = {"dpmpp-2m-sde": sample_dpmpp_2m_sde, "dpmpp-3m-sde": sample_dpmpp_3m_sde}[sampler_type]
+    return fn(den, x, sigmas, extra_args=extra_args, callback=callback, noise_sampler=noise_sampler)

@@ -274,3 +274,42 @@ def test_stream_decode_needs_cuda_latents():
     pcm = float_to_int16_audio(torch.tensor([[0.5, -2.0, 1.0]]))
     assert pcm.dtype == torch.int16 and pcm.tolist() == [[8191, -32767, 16383]]    # peak 2 > 1 -> normalised
     assert float_to_int16_audio(torch.tensor([[0.5, -0.25]]), maximize=True).tolist() == [[32767, -16383]]
+
+
+def test_loading_through_a_parent_module_marks_the_native_weights_stale():
+    """nn.Module.load_state_dict on a parent recurses through _load_from_state_dict and never calls the child's
+    load_state_dict; the native copy must still be refreshed (a post hook on the child sets the flag)."""
+    from stable_audio_tools.models.autoencoders import OobleckDecoder
+    from stable_audio_tools.models.diffusion import DiTWrapper
+    w = DiTWrapper(io_channels=64, embed_dim=256, depth=1, num_heads=4, cond_token_dim=128, global_cond_dim=256,
+                   project_cond_tokens=False, transformer_type="continuous_transformer")
+    w.model.__dict__["_weights_dirty"] = False             # as after a first forward
+    w.load_state_dict(w.state_dict())                       # through the PARENT
+    assert w.model.__dict__["_weights_dirty"] is True
+    holder = torch.nn.ModuleDict({"dec": OobleckDecoder(out_channels=2, channels=32, c_mults=[1, 2], strides=[2, 4],
+                                                        latent_dim=8, use_snake=True, final_tanh=False)})
+    holder["dec"].__dict__["_dirty"] = False
+    holder.load_state_dict(holder.state_dict())
+    assert holder["dec"].__dict__["_dirty"] is True
+
+
+def test_adaptive_solver_reports_every_iteration_with_the_pre_update_estimate():
+    """k-diffusion's dpm_adaptive calls the callback once per iteration (accepted or not) with a running index and
+    denoised = x_old - sigma(s_old) * eps(x_old, s_old)."""
+    from stable_audio_tools.inference.sampling import VDenoiser, sample_dpm_adaptive
+    seen = []
+
+    def model_fn(x, t, **kw):
+        return 0.3 * x
+
+    x0 = torch.randn(1, 2, 8)
+    den = VDenoiser(model_fn)
+
+    def cb(a):
+        seen.append((a["i"], a["x"].clone(), a["denoised"].clone(), float(a["sigma"])))
+
+    sample_dpm_adaptive(den, x0.clone() * 5.0, 0.3, 5.0, callback=cb, rtol=0.01, atol=0.01)
+    assert [s[0] for s in seen] == list(range(len(seen))) and len(seen) >= 2
+    first = seen[0]
+    expect = den(x0 * 5.0, torch.tensor([5.0]))              # the estimate at the initial state / sigma_max
+    assert torch.allclose(first[2], expect, atol=1e-5)

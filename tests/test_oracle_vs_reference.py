@@ -130,3 +130,32 @@ def test_number_conditioner_and_multiconditioner_match_reference(ref):
     mc = mine.MultiConditioner({"seconds_start": b, "seconds_total": mine.NumberConditioner(64, 0, 512)})
     out = mc([{"seconds_start": 0, "seconds_total": [30]}, {"seconds_start": 1, "seconds_total": 47}])
     assert out["seconds_total"][0].shape == (2, 1, 64)
+
+
+def test_oracle_sample_k_inpainting_and_mask_vs_live_reference(ref):
+    """oracle.sampler_oracle.sample_k / build_mask / cut_paste (used by the GPU init-audio test as the checker)
+    against the reference's own sample_k (inference/sampling.py:144-228) and build_mask (generation.py:270-292):
+    same toy denoiser, every random draw (SDE noise and the inpainting callback's re-noising) from one seeded
+    stream via a patched torch.randn_like."""
+    from oracle import sampler_oracle as so
+    from oracle.make_golden import seeded_randn_like
+    margs = dict(cropfrom=10.0, pastefrom=20.0, pasteto=90.0, maskstart=25.0, maskend=80.0, softnessL=12.0,
+                 softnessR=7.0, marination=0.2)
+    L = 48
+    assert torch.equal(so.build_mask(L, margs), ref.generation.build_mask(L, margs))
+    torch.manual_seed(0)
+    w = torch.randn(4, 4) * 0.3
+
+    def toy(x, t, **kw):
+        return torch.einsum("ij,bjl->bil", w, x) * (1 + t[:, None, None])
+
+    noise, init = torch.randn(2, 4, L), torch.randn(2, 4, L)
+    mask = so.build_mask(L, margs)
+    for st in ("dpmpp-2m-sde", "dpmpp-3m-sde"):
+        for m in (mask, None):
+            with seeded_randn_like(5):
+                a = ref.sampling.sample_k(toy, noise.clone(), init.clone(), m, steps=7, sampler_type=st, sigma_min=0.3,
+                                          sigma_max=20, device="cpu")
+            with seeded_randn_like(5):
+                b = so.sample_k(toy, noise.clone(), init.clone(), m, steps=7, sampler_type=st, sigma_min=0.3, sigma_max=20)
+            assert rel_l2(b, a) < 1e-6
