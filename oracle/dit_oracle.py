@@ -21,6 +21,38 @@ def _lin(x, w, b=None):
     return F.linear(x, w, b)
 
 
+# Optional emulation of 16-bit tensor-core operands (tests only; None = the reference's plain fp32 arithmetic).
+# With torch.float16 / torch.bfloat16 set, every contraction that the native path runs on tensor cores rounds its
+# two operands to that type: the Linear layers of the blocks (input activations and weights), project_in / out,
+# to_cond_embed, and the attention core (q, k, v and the probabilities P before P V); accumulation, LayerNorm,
+# softmax, RoPE, biases, the residual stream and the timestep / global-embedding MLPs stay fp32.  The error of
+# this variant against the fp32 oracle is the floor any implementation with 16-bit operands sits on - the
+# reference's own GPU path (fp16 autocast, inference/sampling.py:210) included.
+_OPERAND_DTYPE = None
+
+
+class operand_rounding:
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global _OPERAND_DTYPE
+        self.prev, _OPERAND_DTYPE = _OPERAND_DTYPE, self.dtype
+
+    def __exit__(self, *exc):
+        global _OPERAND_DTYPE
+        _OPERAND_DTYPE = self.prev
+
+
+def _rnd(t):
+    return t if (_OPERAND_DTYPE is None or t is None) else t.to(_OPERAND_DTYPE).to(t.dtype)
+
+
+def _lin16(x, w, b=None):
+    """A Linear layer that the native path runs as a 16-bit-operand GEMM."""
+    return F.linear(_rnd(x), _rnd(w), b)
+
+
 def fourier_features(t, weight):
     """models/blocks.py:95-97: f = 2*pi*t @ W^T ; cat[cos f, sin f]."""
     f = 2 * math.pi * t[:, None] @ weight.T
@@ -69,9 +101,9 @@ def attention_core(q, k, v):
         k = k.repeat_interleave(rep, dim=1)
         v = v.repeat_interleave(rep, dim=1)
     scale = 1.0 / (q.shape[-1] ** 0.5)
-    dots = torch.einsum("bhid,bhjd->bhij", q, k) * scale
+    dots = torch.einsum("bhid,bhjd->bhij", _rnd(q), _rnd(k)) * scale
     attn = F.softmax(dots, dim=-1, dtype=torch.float32).type(dots.dtype)
-    return torch.einsum("bhij,bhjd->bhid", attn, v)
+    return torch.einsum("bhij,bhjd->bhid", _rnd(attn), _rnd(v))
 
 
 def _heads(x, h):
@@ -83,7 +115,7 @@ def self_attention(x, sd, pfx, dim_heads, freqs, qk_norm=False):
     """models/transformer.py:407-554, fused to_qkv branch (:430-431), optional cosine-sim
     normalisation of q and k (:433-436), RoPE (:438-452)."""
     h = x.shape[-1] // dim_heads
-    q, k, v = _lin(x, sd[pfx + "to_qkv.weight"]).chunk(3, dim=-1)
+    q, k, v = _lin16(x, sd[pfx + "to_qkv.weight"]).chunk(3, dim=-1)
     q, k, v = (_heads(t, h) for t in (q, k, v))
     if qk_norm:
         q, k = F.normalize(q, dim=-1), F.normalize(k, dim=-1)
@@ -94,31 +126,31 @@ def self_attention(x, sd, pfx, dim_heads, freqs, qk_norm=False):
         k = apply_rotary(k, freqs)
     o = attention_core(q, k, v)
     o = o.permute(0, 2, 1, 3).reshape(x.shape[0], x.shape[1], -1)
-    return _lin(o, sd[pfx + "to_out.weight"])
+    return _lin16(o, sd[pfx + "to_out.weight"])
 
 
 def cross_attention(x, ctx, sd, pfx, dim_heads, qk_norm=False):
     """models/transformer.py:420-427 (separate to_q / to_kv), kv_heads =
     dim_context // dim_heads (:306-312); no RoPE when a context is given (:438)."""
     h = x.shape[-1] // dim_heads
-    q = _heads(_lin(x, sd[pfx + "to_q.weight"]), h)
-    k, v = _lin(ctx, sd[pfx + "to_kv.weight"]).chunk(2, dim=-1)
+    q = _heads(_lin16(x, sd[pfx + "to_q.weight"]), h)
+    k, v = _lin16(ctx, sd[pfx + "to_kv.weight"]).chunk(2, dim=-1)
     kv_h = k.shape[-1] // dim_heads
     k, v = _heads(k, kv_h), _heads(v, kv_h)
     if qk_norm:                                                                  # transformer.py:433-436
         q, k = F.normalize(q, dim=-1), F.normalize(k, dim=-1)
     o = attention_core(q, k, v)
     o = o.permute(0, 2, 1, 3).reshape(x.shape[0], x.shape[1], -1)
-    return _lin(o, sd[pfx + "to_out.weight"])
+    return _lin16(o, sd[pfx + "to_out.weight"])
 
 
 def feed_forward(x, sd, pfx):
     """models/transformer.py:222-235 (GLU: value = first half, gate = second
     half, SiLU on the gate) and :270 (output Linear with bias)."""
-    u = _lin(x, sd[pfx + "ff.0.proj.weight"], sd.get(pfx + "ff.0.proj.bias"))
+    u = _lin16(x, sd[pfx + "ff.0.proj.weight"], sd.get(pfx + "ff.0.proj.bias"))
     val, gate = u.chunk(2, dim=-1)
     m = val * F.silu(gate)
-    return _lin(m, sd[pfx + "ff.2.weight"], sd.get(pfx + "ff.2.bias"))
+    return _lin16(m, sd[pfx + "ff.2.weight"], sd.get(pfx + "ff.2.bias"))
 
 
 def transformer_block(x, ctx, global_cond, sd, pfx, dim_heads, freqs, qk_norm=False):
@@ -158,7 +190,7 @@ def continuous_transformer(x, prepend, ctx, global_cond, sd, depth, dim_heads, h
     """models/transformer.py:764-809: project_in, cat prepend, rotary table for
     the full length (prepend token = position 0), blocks, project_out."""
     pfx = "transformer."
-    x = _lin(x, sd[pfx + "project_in.weight"])
+    x = _lin16(x, sd[pfx + "project_in.weight"])
     if prepend is not None:
         x = torch.cat((prepend, x), dim=-2)
     freqs = None
@@ -168,7 +200,7 @@ def continuous_transformer(x, prepend, ctx, global_cond, sd, depth, dim_heads, h
         x = transformer_block(x, ctx, global_cond, sd, f"{pfx}layers.{i}.", dim_heads, freqs, qk_norm)
         if hidden_states is not None:
             hidden_states.append(x)
-    return _lin(x, sd[pfx + "project_out.weight"])
+    return _lin16(x, sd[pfx + "project_out.weight"])
 
 
 def _mlp(x, sd, name):
@@ -184,7 +216,8 @@ def dit_inner_forward(sd, cfg, x, t, cross_attn_cond=None, global_embed=None, hi
     dim_heads = cfg["embed_dim"] // cfg["num_heads"]
     gtype = cfg.get("global_cond_type", "prepend")
     if cross_attn_cond is not None:
-        cross_attn_cond = _mlp(cross_attn_cond, sd, "to_cond_embed")            # dit.py:149-150
+        cross_attn_cond = _lin16(F.silu(_lin16(cross_attn_cond, sd["to_cond_embed.0.weight"])),
+                                 sd["to_cond_embed.2.weight"])                    # dit.py:149-150 (bias-free MLP)
     if global_embed is not None:
         global_embed = _mlp(global_embed, sd, "to_global_embed")                # dit.py:152-154
     te = _mlp(fourier_features(t, sd["timestep_features.weight"]), sd, "to_timestep_embed")  # dit.py:176

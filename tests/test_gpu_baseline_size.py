@@ -4,8 +4,10 @@ configs[0] exactly (mono 16 kHz chunked reconstruct, against the real reference'
 init-audio / inpainting branch of generate_diffusion_cond.
 
 Tolerances (fp16 operands, fp32 accumulation / residual stream, vs the fp32 oracle):
-  * DiT output: rel-L2 <= 2e-3 * max(1, cfg_scale / 1.5) (the CFG combine u + (c - u) s amplifies the difference of two
-    nearly equal forwards by ~s);
+  * DiT output at reduced depth: rel-L2 <= 2e-3 * max(1, cfg_scale / 1.5) (the CFG combine u + (c - u) s amplifies the
+    difference of two nearly equal forwards by ~s); at the full 24 blocks the fp16 rounding of the GEMM operands alone
+    reaches 2.7e-3 (no CFG), so there the gate is "within 1.25 x of the fp16-operand floor measured with the oracle
+    (dit_oracle.operand_rounding) and <= 4e-3";
   * Oobleck: within 2x of the operand-rounding floor measured with the oracle itself (same fp32 arithmetic with conv
     operands rounded to fp16), and the audio-domain SNR in dB is reported.
 Every measured number is appended to gpurun_out/parity_sizes.jsonl (when that directory exists) so that the
@@ -48,16 +50,22 @@ def test_sao_dit_all_24_blocks_cfg7_vs_oracle(t_val):
     x, t = torch.randn(1, 64, 1024, generator=g), torch.tensor([t_val])
     c, ge = torch.randn(1, 130, 768, generator=g), torch.randn(1, 1536, generator=g)
     c[:, 40:128] = 0.0                                  # padded T5 rows are exact zeros (conditioners.py:343-344)
+    fwd = lambda s: do.dit_forward(sd, SAO_DIT, x, t, cross_attn_cond=c, global_embed=ge, cfg_scale=s)
     t0 = time.time()
-    ref = do.dit_forward(sd, SAO_DIT, x, t, cross_attn_cond=c, global_embed=ge, cfg_scale=7.0)
-    ref1 = do.dit_forward(sd, SAO_DIT, x, t, cross_attn_cond=c, global_embed=ge, cfg_scale=1.0)
+    ref, ref1 = fwd(7.0), fwd(1.0)
     oracle_s = time.time() - t0
+    with do.operand_rounding(torch.float16):          # the floor of ANY fp16-operand implementation (the reference's
+        floor7, floor1 = rel_l2(fwd(7.0), ref), rel_l2(fwd(1.0), ref1)    # own autocast GPU path included)
     m = build_native_dit(SAO_DIT, sd)
     run = lambda s: m(x.cuda(), t.cuda(), cross_attn_cond=c.cuda(), global_embed=ge.cuda(), cfg_scale=s).cpu()
     e7, e1 = rel_l2(run(7.0), ref), rel_l2(run(1.0), ref1)
-    report("sao_dit_24_blocks", t=t_val, rel_l2_cfg7=e7, rel_l2_nocfg=e1, oracle_s=oracle_s)
-    assert e1 < 2e-3, e1
-    assert e7 < 2e-3 * 7.0 / 1.5, e7
+    report("sao_dit_24_blocks", t=t_val, rel_l2_cfg7=e7, rel_l2_nocfg=e1, fp16_operand_floor_cfg7=floor7,
+           fp16_operand_floor_nocfg=floor1, oracle_s=oracle_s)
+    # Through 24 blocks the rounding of the GEMM operands to fp16 alone costs 2.7e-3 (no CFG) / 5.9e-3 (CFG 7) against
+    # the fp32 oracle (measured with the oracle itself); the native path must sit on that floor (<= 1.25 x) and inside
+    # the stated absolute tolerance: 4e-3 without CFG, 4e-3 * cfg_scale / 1.5 ... capped by the same ratio with CFG.
+    assert e1 < 1.25 * floor1 and e1 < 4e-3, (e1, floor1)
+    assert e7 < 1.25 * floor7 and e7 < 2e-3 * 7.0 / 1.5, (e7, floor7)
 
 
 def test_sao_dit_24_blocks_batch4_rows_match_single_prompt_rows():
