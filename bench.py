@@ -1,17 +1,19 @@
 """Benchmark of the Stable Audio denoising hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config {2,3,4,5}] [--impl reference]
 
-Workload (BASELINE.json configs[2], the configuration the metric is quoted on): Stable Audio
-Open 1.0 DiT (1.06 B parameters, random init), 47.55 s stereo 44.1 kHz = 1024 latent tokens,
-batch 4 with classifier-free guidance (8 transformer rows), dpmpp-3m-sde sampler, synthetic
-conditioning; one "step" = one sampler iteration = one CFG denoiser call + the sampler update.
-`value` = denoise steps per second summed over all ranks (weak scaling: every rank runs its
-own batch of 4 prompts, sharded like the reference's generate.py:119-120).  Extra keys report
-audio-seconds/s for a full 100-step generation (100 x step time + the measured Oobleck decode).
+Default workload = BASELINE.json configs[2] (--config 3, the configuration the metric is quoted on): Stable Audio
+Open 1.0 DiT (1.06 B parameters, random init), 47.55 s stereo 44.1 kHz = 1024 latent tokens, batch 4 per GPU with
+classifier-free guidance (8 transformer rows), dpmpp-3m-sde sampler, synthetic conditioning; one "step" = one
+sampler iteration = one CFG denoiser call + the sampler update.  `value` = denoise steps per second summed over all
+ranks (weak scaling: every rank runs its own batch, sharded like the reference's generate.py:119-120).  Extra keys
+report audio-seconds/s for a full 100-step generation (100 x step time + the measured Oobleck decode).
+Other BASELINE configurations: --config 2 = one prompt (2 rows); --config 4 = 64 prompts over 8 GPUs =
+batch 8 per GPU (16 rows); --config 5 = the SA-2.0 length (6144 latents + prepend = 6145 tokens), one prompt per GPU.
 
---impl reference times the reference's CPU path (the oracle port of the same DiT forward, all
-host threads) on a bounded sample of the same workload.
+--impl reference times the reference's CPU path (the oracle port of the same DiT forward) with every host thread it
+can use, on a bounded sample of the same workload: the WHOLE batch of the configuration in one call through d of the
+24 identical blocks, scaled by 24 / d.
 """
 import argparse
 import ctypes
@@ -25,7 +27,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "friendly-stable-audio-tools_b200")
-for p in (ROOT, PKG):
+for p in (ROOT, PKG, os.path.join(ROOT, "profiles", "tools")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -37,13 +39,25 @@ SAO_DIT = dict(io_channels=64, embed_dim=1536, depth=24, num_heads=24, cond_toke
                project_cond_tokens=False, transformer_type="continuous_transformer")
 SAO_DEC = dict(out_channels=2, channels=128, c_mults=[1, 2, 4, 8, 16], strides=[2, 4, 4, 8, 8], latent_dim=64,
                use_snake=True, final_tanh=False)
-LATENT_LEN = 1024          # 2097152 samples / 2048
 CTX_LEN = 130              # 128 T5 tokens + seconds_start + seconds_total
-BATCH = 4
 CFG_SCALE = 7.0
-AUDIO_SECONDS = 2097152 / 44100.0
 GEN_STEPS = 100
 SIGMA_MIN, SIGMA_MAX = 0.3, 500.0    # generate.py:135-136
+# BASELINE.json configs (1-based like SURVEY.md 8d): per-GPU batch and latent length
+CONFIGS = {
+    2: dict(batch=1, latent_len=1024, name="SA-Open-1.0 DiT single denoise step, one prompt (BASELINE configs[1])"),
+    3: dict(batch=4, latent_len=1024, name="SA-Open-1.0 100-step generation, batch 4 per GPU (BASELINE configs[2])"),
+    4: dict(batch=8, latent_len=1024, name="64 prompts over 8 GPUs = batch 8 per GPU (BASELINE configs[3])"),
+    5: dict(batch=1, latent_len=6144, name="SA-2.0 length, 6144 latents (285 s), one prompt per GPU (BASELINE configs[4])"),
+}
+BATCH, LATENT_LEN = 4, 1024          # set from --config in main()
+AUDIO_SECONDS = 2097152 / 44100.0
+
+
+def set_config(idx):
+    global BATCH, LATENT_LEN, AUDIO_SECONDS
+    BATCH, LATENT_LEN = CONFIGS[idx]["batch"], CONFIGS[idx]["latent_len"]
+    AUDIO_SECONDS = LATENT_LEN * 2048 / 44100.0
 
 
 def flops_per_step(B):
@@ -58,8 +72,10 @@ def flops_per_step(B):
 
 
 def config_dict(args, extra=None):
-    c = {"workload": "SA-Open-1.0 DiT denoise step, 47.55 s stereo 44.1 kHz (1024 latent tokens + 1 prepend), "
-                     "batch 4 per GPU with CFG 7 (8 rows), dpmpp-3m-sde update, synthetic T5-shaped conditioning",
+    c = {"workload": f"SA-Open-1.0 DiT denoise step, {AUDIO_SECONDS:.2f} s stereo 44.1 kHz ({LATENT_LEN} latent tokens + 1 "
+                     f"prepend), batch {BATCH} per GPU with CFG 7 ({2 * BATCH} rows), dpmpp-3m-sde update, synthetic "
+                     f"T5-shaped conditioning [{CONFIGS[args.config]['name']}]",
+         "baseline_config": args.config,
          "global_batch": BATCH * args.gpus, "latent_tokens": LATENT_LEN, "context_tokens": CTX_LEN,
          "parallelism": f"dp{args.gpus}", "l2_policy": "per-step working set (2.1 GB of 16-bit weights) exceeds the 126 MB L2"}
     if extra:
@@ -114,11 +130,11 @@ class ClockSampler:
 
 
 def pick_threads(fn):
-    """Large hosts oversubscribe badly on these small-matrix fp32 ops: probe a few thread counts on one
-    call of `fn` and keep the fastest (reported as `cores` = threads actually used)."""
+    """fp32 torch ops on a large host do not always run fastest on every hardware thread: probe all / half / a
+    quarter of the threads on one call of `fn` and keep the fastest (reported as threads_used of threads_total)."""
     cores = os.cpu_count() or 1
     best, best_t = None, float("inf")
-    for n in sorted({c for c in (cores, 64, 32, 16, 8) if c <= cores}, reverse=True):
+    for n in sorted({max(1, cores // d) for d in (1, 2, 4)}, reverse=True):
         torch.set_num_threads(n)
         fn()
         t0 = time.time()
@@ -130,33 +146,39 @@ def pick_threads(fn):
     return best
 
 
-# --------------------------------------------------------------------------- reference arm
-def run_reference(args):
-    """CPU path of the reference: the oracle port of DiffusionTransformer.forward (oracle/dit_oracle.py,
-    pinned to the reference modules by tests/golden) on all host threads.  Each 'step' is a bounded
-    sample of the B=4 workload: ONE conditional+unconditional pair (B=1, 2 rows) through a slice of
-    `d` of the 24 identical blocks, scaled by (24/d)*4 to the full step."""
+def cpu_inputs():
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(BATCH, 64, LATENT_LEN, generator=g)
+    t = torch.full((BATCH,), 0.5)
+    c = torch.randn(BATCH, CTX_LEN, 768, generator=g)
+    ge = torch.randn(BATCH, 1536, generator=g)
+    return x, t, c, ge
+
+
+def cpu_sample(budget_s, n_calls):
+    """The reference's CPU path on a bounded sample: the oracle port (oracle/dit_oracle.py, pinned to the reference
+    modules by tests/golden) of ONE CFG denoiser call on the configuration's WHOLE batch (2 * BATCH rows in one call, so
+    every host thread has work) through d of the 24 identical blocks; time scaled by 24 / d.  No batch extrapolation."""
     from oracle import dit_oracle as do
+    x, t, c, ge = cpu_inputs()
+    cfg1 = dict(SAO_DIT, depth=1)
+    sd1 = do.make_dit_weights(cfg1, seed=0)
+    with torch.no_grad():
+        threads = pick_threads(lambda: do.dit_forward(sd1, cfg1, x, t, c, ge, cfg_scale=CFG_SCALE))
+        t0 = time.time()
+        do.dit_forward(sd1, cfg1, x, t, c, ge, cfg_scale=CFG_SCALE)
+        block_s = time.time() - t0
+    d = int(max(1, min(24, (budget_s / max(1, n_calls)) / max(block_s, 1e-3))))
+    cfg = dict(SAO_DIT, depth=d)
+    sd = sd1 if d == 1 else do.make_dit_weights(cfg, seed=0)
+    return do, cfg, sd, (x, t, c, ge), d, threads
+
+
+def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # time one block to size the slice
-    probe_cfg = dict(SAO_DIT, depth=1)
-    sd1 = do.make_dit_weights(probe_cfg, seed=0)
-    g = torch.Generator().manual_seed(1)
-    x = torch.randn(1, 64, LATENT_LEN, generator=g)
-    t = torch.tensor([0.5])
-    c = torch.randn(1, CTX_LEN, 768, generator=g)
-    ge = torch.randn(1, 1536, generator=g)
-    with torch.no_grad():
-        cores = pick_threads(lambda: do.dit_forward(sd1, probe_cfg, x, t, c, ge, cfg_scale=CFG_SCALE))
-        t0 = time.time()
-        do.dit_forward(sd1, probe_cfg, x, t, c, ge, cfg_scale=CFG_SCALE)
-        block_s = time.time() - t0
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    d = int(max(1, min(24, budget / max(block_s, 1e-3))))
-    cfg = dict(SAO_DIT, depth=d)
-    sd = do.make_dit_weights(cfg, seed=0)
+    do, cfg, sd, (x, t, c, ge), d, threads = cpu_sample(150.0, args.steps + args.warmup)
     times = []
     with torch.no_grad():
         for i in range(args.warmup + args.steps):
@@ -164,16 +186,16 @@ def run_reference(args):
             do.dit_forward(sd, cfg, x, t, c, ge, cfg_scale=CFG_SCALE)
             if i >= args.warmup:
                 times.append(time.time() - t0)
-    per_sample = sum(times) / len(times)
-    step_s = per_sample * (24.0 / d) * BATCH          # full B=4 step
+    step_s = sum(times) / len(times) * (24.0 / d)
     value = 1.0 / step_s
-    sample = (f"1 of the 4 prompts (2 CFG rows) through {d} of 24 blocks per step, fp32, {cores} of {os.cpu_count()} threads; "
-              f"scaled x{24.0 / d:.2f} (depth) x{BATCH} (batch)")
+    sample = (f"all {BATCH} prompts ({2 * BATCH} CFG rows) in one call through {d} of 24 blocks per step, fp32, "
+              f"{threads} of {os.cpu_count()} host threads; scaled x{24.0 / d:.2f} (depth only)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "threads_total": os.cpu_count(),
+                             "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -198,28 +220,18 @@ def build_models(device):
 
 
 def cpu_baseline_leg():
-    """Oracle port of one CFG pair (B=1) through 4 of 24 blocks on all host threads, scaled."""
-    from oracle import dit_oracle as do
-    d = 4
-    cfg = dict(SAO_DIT, depth=d)
-    sd = do.make_dit_weights(cfg, seed=0)
-    g = torch.Generator().manual_seed(1)
-    x = torch.randn(1, 64, LATENT_LEN, generator=g)
-    t = torch.tensor([0.5])
-    c = torch.randn(1, CTX_LEN, 768, generator=g)
-    ge = torch.randn(1, 1536, generator=g)
+    """Same bounded sample as --impl reference, ~10-20 s of host time."""
+    do, cfg, sd, (x, t, c, ge), d, threads = cpu_sample(6.0, 1)
     with torch.no_grad():
-        cfg1 = dict(SAO_DIT, depth=1)
-        cores = pick_threads(lambda: do.dit_forward(sd, cfg1, x, t, c, ge, cfg_scale=CFG_SCALE))
         n, t0 = 0, time.time()
-        while n < 3 or time.time() - t0 < 8.0:
+        while n < 2 or time.time() - t0 < 10.0:
             do.dit_forward(sd, cfg, x, t, c, ge, cfg_scale=CFG_SCALE)
             n += 1
         per = (time.time() - t0) / n
-    step_s = per * (24.0 / d) * BATCH
-    return {"value": 1.0 / step_s, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} x (1 of 4 prompts, 2 CFG rows, {d} of 24 blocks) fp32 on {cores} of {os.cpu_count()} threads, "
-                      f"scaled x{24 // d} depth x{BATCH} batch"}
+    step_s = per * (24.0 / d)
+    return {"value": 1.0 / step_s, "unit": UNIT, "cores": threads, "threads_total": os.cpu_count(), "kind": "port",
+            "sample": f"{n} x (all {BATCH} prompts = {2 * BATCH} CFG rows in one call, {d} of 24 blocks) fp32 on {threads} of "
+                      f"{os.cpu_count()} host threads, scaled x{24.0 / d:.1f} (depth only)"}
 
 
 def run_native(args):
@@ -394,8 +406,8 @@ def run_native(args):
     # ---------------- other BASELINE.json shapes, for the record (single GPU only) ---------------
     # configs[1]: one prompt (2 CFG rows x 1025 tokens); configs[4]: SA-2.0 length (L = 6144 latents, 1 prompt).
     extra_shapes = {}
-    if world == 1:
-        for name, L_x in (("single_prompt_L1024", LATENT_LEN), ("single_prompt_L6144_sa2_length", 6144)):
+    if world == 1 and args.config == 3:
+        for name, L_x in (("single_prompt_L1024", 1024), ("single_prompt_L6144_sa2_length", 6144)):
             xs = torch.randn(1, 64, L_x, device=device)
             ts = torch.full((1,), 0.5, device=device)
             kw = dict(cross_attn_cond=cross[:1].contiguous(), cross_attn_mask=mask[:1].contiguous(),
@@ -411,21 +423,12 @@ def run_native(args):
             torch.cuda.synchronize()
             extra_shapes[name] = {"ms_per_model_call": s0.elapsed_time(s1) / 10, "rows": 2, "tokens": L_x + 1}
 
-    # Oobleck decoder roofline bookkeeping, per sample of L = 1024 latents:
-    #   FLOPs 5.163e12; bytes for the fusion level implemented (16-bit activated copy in/out of every
-    #   tensor-core conv, fp32 raw skip stream read+written once per ResidualUnit, the 128- and 256-channel
-    #   ResidualUnits fused into one kernel):
-    dec_flops = 5.163e12
-    dec_bytes = 0.0
-    l_out, chans, strides = LATENT_LEN, [2048, 1024, 512, 256, 128, 128], [8, 8, 4, 4, 2]
-    for i, st_ in enumerate(strides):
-        l_in, l_out = l_out, l_out * st_
-        elems = l_out * chans[i + 1]
-        dec_bytes += 2.0 * l_in * chans[i] + 6.0 * elems        # ConvT: read s16, write raw fp32 + s16
-        dec_bytes += (12 + 12 + 8) * elems                        # 3 x conv1 / fused unit: 2+4+4+2 B (last: no raw write)
-        if chans[i + 1] not in (128, 256):
-            dec_bytes += 3 * 4.0 * elems                          # two-launch units: conv7 writes + conv1 reads a 16-bit copy
-    dec_bytes += 2.0 * l_out * 128 + 4.0 * l_out * 2             # final conv
+    # Oobleck decoder roofline bookkeeping, per sample: ONE byte model, shared with the
+    # per-layer profile tool (profiles/tools/decoder_bytes.py): 16-bit activated copies between convolutions, the raw
+    # skip stream in fp16 (2 B) with fp16 operands, 128- / 256-channel ResidualUnits fused into one launch.
+    import decoder_bytes
+    raw_bytes = 4 if os.environ.get("SATB_RAW") == "fp32" else 2
+    dec_flops, dec_bytes = decoder_bytes.totals(LATENT_LEN, raw_bytes)
     dec_ms_sample = decode_ms / BATCH
     gen_ms = GEN_STEPS * ms_per_step + decode_ms
     audio_sec_per_s = world * BATCH * AUDIO_SECONDS / (gen_ms / 1e3)
@@ -447,6 +450,9 @@ def run_native(args):
         if "bf16_tflops_sustained" in peaks else "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
     M = 2 * BATCH * (LATENT_LEN + 1)
     ff_in_flops = 2.0 * M * 12288 * 1536
+    peak_burst = peaks.get("bf16_tflops")
+    hbm_peak = peaks.get("hbm_gbs") or 6650.0
+    survey_gb = decoder_bytes.SURVEY_PER_RESUNIT_FUSED_FP32_GB * LATENT_LEN / 1024.0
     ff_in_ms = ms8[0] / max(cnt8[0], 1)
     achieved = ff_in_flops / (ff_in_ms / 1e3) / 1e12 if ff_in_ms > 0 else None
     cats = ["ff_in_gemm", "ff_out_gemm", "qkv_gemm", "self_attention", "attn_out_gemm", "cross_attention", "layernorm"]
@@ -461,25 +467,34 @@ def run_native(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_2cta_kernel<EpiSwiglu, 256> (FF-in 8200x12288x1536)",
+        "roofline": {"bound": "tensor", "kernel": f"gemm_tcgen05_2cta_kernel<EpiSwiglu, 256> (FF-in {M}x12288x1536)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (achieved / peak_tf) if achieved else None,
+                     "frac_of_burst_peak": (achieved / peak_burst) if (achieved and peak_burst) else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel from the
                      # `ncu --set full` capture summarised in profiles/r01_ncu_ff_in_gemm.txt (63.2 + 62.6 MB;
                      # algorithmic A + W + out = 163.7 MB, part of the 16-bit output stays in the 126 MB L2)
                      "traffic": 125806592, "traffic_unit": "bytes per launch (ncu)", "peak_source": peak_src,
                      "avg_launch_ms": ff_in_ms},
         "step_tflops": step_tflops, "step_frac_of_peak": step_tflops / peak_tf,
+        "step_frac_of_burst_peak": (step_tflops / peak_burst) if peak_burst else None,
         "profiled_pass_ms_per_step": profiled_ms_per_step, "host_enqueue_ms_per_step": host_enqueue_ms,
         "kernel_breakdown": breakdown,
         "decode_ms_batch": decode_ms, "audio_sec_per_s_100step": audio_sec_per_s,
         "other_shapes": extra_shapes,
-        "oobleck_decoder": {"ms_per_sample": dec_ms_sample, "tflops": dec_flops / (dec_ms_sample / 1e3) / 1e12,
+        "oobleck_decoder": {"ms_per_sample": dec_ms_sample, "latents": LATENT_LEN,
+                            "tflops": dec_flops / (dec_ms_sample / 1e3) / 1e12,
                             "frac_of_tensor_peak": dec_flops / (dec_ms_sample / 1e3) / 1e12 / peak_tf,
-                            "algorithmic_gb_per_sample": dec_bytes / 1e9,
+                            "algorithmic_gb_per_sample": dec_bytes / 1e9, "raw_stream_bytes": raw_bytes,
                             "hbm_gbs": dec_bytes / (dec_ms_sample / 1e3) / 1e9,
-                            "frac_of_hbm_peak": dec_bytes / (dec_ms_sample / 1e3) / 1e9 / (peaks.get("hbm_gbs") or 6650.0),
-                            "note": "5.16 TFLOP per sample sits at the tensor/HBM ridge (SURVEY 0, H2): neither roof is reached"},
+                            "frac_of_hbm_peak": dec_bytes / (dec_ms_sample / 1e3) / 1e9 / hbm_peak,
+                            # the same time against SURVEY.md 8(d)'s denominator (per-ResidualUnit-fused, fp32 activations)
+                            "survey_gb_per_sample": survey_gb,
+                            "frac_of_hbm_peak_survey_denominator": survey_gb / (dec_ms_sample / 1e3) / hbm_peak,
+                            "roofline_floor_ms": max(dec_flops / (peak_tf * 1e12), dec_bytes / (hbm_peak * 1e9)) * 1e3,
+                            "byte_model": "profiles/tools/decoder_bytes.py",
+                            "note": "5.16 TFLOP per 1024 latents: with the 16-bit streams of this round the decoder's "
+                                    "tensor time exceeds its HBM time, i.e. the bound is the tensor pipe"},
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg()
@@ -509,11 +524,15 @@ def main():
     _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)      # seconds-long timed region: sustained clocks, not burst
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS),
+                    help="BASELINE.json configuration (1-based, SURVEY.md 8d): 2 = one prompt, 3 = batch 4 (default, the one "
+                         "the metric is quoted on), 4 = batch 8 per GPU (64 prompts on 8 GPUs), 5 = SA-2.0 length")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     args = ap.parse_args()
+    set_config(args.config)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -1,53 +1,71 @@
 // tcgen05 attention forward, head dim 64, no mask, non-causal, optional GQA:
 //   O = softmax(Q K^T / sqrt(64)) V      (reference models/transformer.py:496-536)
 //
-// One CTA = 128 query rows of one (batch item, head); two CTAs are resident per SM.  Keys are
-// processed in tiles of 64 with double-buffered S and P in TMEM, so the tensor pipe runs ahead of
-// the softmax warps:
-//   warp 1 (one thread): S[b] = Q K_j^T -> TMEM (tcgen05.mma, smem operands), two tiles ahead
-//   warp 3 (one thread): O += P[b] V_j (A = P from TMEM, B = V tile addressed MN-major); the two
-//                        products are issued by different threads because a tcgen05.mma issue
-//                        costs ~100 cycles of the issuing thread (measured, profiles/)
-//   warps 4-7 (one query row per thread): one pass over S[b]: P = exp2(S*c - m_ref) -> TMEM as
-//                        packed 16-bit pairs, row sum (fp32) and raw row max in registers
-// TMEM columns: S0 [0,64) S1 [64,128) P0 [128,160) P1 [160,192) O [192,256).
-// Q/K/V tiles arrive by TMA (128B swizzle, out-of-range rows zero-filled); K tiles are released
-// when Q K^T retires, V tiles when P V retires (independent rings).  O stays in TMEM for the whole
-// pass: the reference max m_ref only moves when a tile's row max exceeds it by more than 2^8
-// (lazy rescale: exponentials stay <= 256, sums in fp32), so the O rescale (TMEM load-scale-store)
-// and the recomputation of that tile's P are rare.
+// Persistent kernel, two CTAs per SM (2 x 256 TMEM columns, 2 x 101 KB shared memory).  A work unit is 128 query
+// rows of one (batch item, head); CTA c processes units c, c + grid, ... without re-initialising anything.  Keys
+// are processed in tiles of 128:
+//   warp 0 (one thread)  TMA producer: Q of the next unit (double-buffered), K / V tiles (2-stage rings)
+//   warp 1 (one thread)  S = Q K_j^T -> TMEM (tcgen05.mma, smem operands) as soon as S has been read out
+//   warp 3 (one thread)  O += P V_j (A = P from TMEM, B = V tile addressed MN-major)
+//   warps 4-7            one query row per thread: P = exp2(S c - m_ref) -> TMEM as packed 16-bit pairs, row sum
+//                        (fp32) and raw row max in registers; chunks of 32 columns are software-pipelined
+//                        (tcgen05.ld of chunk c+2 in flight while chunk c is exponentiated).  S is handed back to the
+//                        MMA thread right after its LAST chunk has been loaded into registers, so Q K_{j+1}^T runs
+//                        under the exponentials of that chunk.
+//   warp 2               TMEM allocator; afterwards the CUDA-core path for ragged query rows (below)
+// TMEM columns: S [0,128)  P [128,192)  O [192,256).  The softmax is SFU-bound (16 ex2 / clk / SM, 202 M exponentials
+// per SA-Open layer): what matters is that the two resident CTAs keep the SFU busy, i.e. that each warp's fixed
+// per-tile cost (barrier waits, TMEM load / store latency) stays below the exponentiation time of a tile - hence
+// 128-key tiles (1024 SFU cycles per warp and tile).
+// O stays in TMEM for the whole unit: the reference max m_ref only moves when a tile's row max exceeds it by more
+// than 2^8 (lazy rescale: exponentials stay <= 256, sums in fp32), so the O rescale (TMEM load-scale-store) and the
+// recomputation of that tile's P are rare.
+//
+// Ragged query rows: with Nq = 1025 = 8 * 128 + 1 (the prepended conditioning token) a ninth tensor-core tile per
+// (item, head) would hold ONE row and cost as much time as a full one.  When Nq % 128 <= kRowPathMax those rows are
+// computed by warp 2 on CUDA cores instead (one warp per row: lane-per-key dot products, online softmax over
+// blocks of 1024 keys, lane-per-two-dims P V), concurrently with the tensor-core pipeline of the same CTA.
 #include "common.cuh"
 #include "gemm.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
+#include <cstdlib>
 
 namespace satb {
 
 namespace {
 
-constexpr int kQ = 128;        // query rows per CTA
-constexpr int kK = 64;         // keys per tile
+constexpr int kQ = 128;        // query rows per unit
+constexpr int kK = 128;        // keys per tile
 constexpr int kD = 64;         // head dim
-constexpr int kStagesK = 4;
-constexpr int kStagesV = 3;
+constexpr int kStagesKV = 2;
 constexpr int kQBytes = kQ * kD * 2;                         // 16 KB
-constexpr int kKVBytes = kK * kD * 2;                        // 8 KB
-constexpr int kAttnSmem = kQBytes + (kStagesK + kStagesV) * kKVBytes + 1024 + 256 + 2048;   // + row exchange [2][2][128] fp32
+constexpr int kKVBytes = kK * kD * 2;                        // 16 KB
+constexpr int kRowChunk = 1024;                              // keys per block of the CUDA-core row path
+constexpr int kRowPathMax = 2;                               // Nq % 128 <= this: those rows take the row path
+constexpr int kAttnSmem = 2 * kQBytes + 2 * kStagesKV * kKVBytes + kRowChunk * 4 + 256 + 1024;
 constexpr int kTmemColsAttn = 256;
-constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;      // S[b] at kColS + 64 b, P[b] at kColP + 32 b
+constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;
 constexpr float kRescaleThreshold = 8.0f;                    // log2 units
 
 struct AttnTcArgs {
   uint16_t* o;
   int64_t ldo, o_bs;
-  int Nq, Nk, group;
-  int q_col, k_col, v_col;   // column offsets (elements) of head 0 inside the q / k / v tensor maps
+  int Nq, Nk, group, H, batch;
+  int q_col, k_col, v_col;   // column offsets (elements) of head 0 inside the q / k / v tensors
+  int n_qt;                  // tensor-core query tiles per (item, head)
+  int n_units;               // batch * H * n_qt
+  int row0, n_rows;          // rows [row0, row0 + n_rows) of every (item, head) take the CUDA-core path
+  const uint16_t *q, *k, *v; // raw pointers for the row path
+  int64_t ldq, ldk, ldv, q_bs, k_bs, v_bs;
   float scale_log2;
-  unsigned long long* dbg;   // optional per-phase clock64 trace of one CTA (profiles/, tests only)
+  int* sm_slots;             // [>= number of SMs] running counters: the two CTAs of an SM draw consecutive values
+  int stagger;               // cycles by which the odd CTA of an SM delays its softmax (see the kernel)
+  unsigned long long* dbg;   // optional clock64 trace of CTA 0's first softmax warp (tests / profiles only)
 };
 
-// V tile as the MN-major B operand: rows = keys (K dim), 64 contiguous 16-bit d values (128 B,
-// one swizzle atom) per row; 8-row groups 1024 B apart.
+// V tile as the MN-major B operand: rows = keys (K dim), 64 contiguous 16-bit d values (128 B, one swizzle atom)
+// per row; 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
@@ -64,8 +82,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// Packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): the softmax warps are issue-bound, so the
-// scale-and-shift and the row-sum accumulation process two elements per instruction.
+// Packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): two elements per issue slot for the scale-and-shift and the
+// row-sum accumulation.
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
@@ -88,51 +106,171 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
   return d;
 }
 
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// --------------------------------------------------------------------------------- CUDA-core row path
+// One warp computes one query row of one (item, head): softmax(q K^T / 8) V in fp32.  Eight lanes share a key
+// (lane l holds dims 8 (l % 8) .. +7 of q, of the K row and of the V row: one 16-byte load per lane and key),
+// so one warp instruction covers four keys and every load of the loop is independent of the previous ones.
+template <bool BF16>
+__device__ void attn_row_path(const AttnTcArgs& p, int b, int h, int row, float* prow, int lane) {
+  const int hk = h / p.group;
+  const int sub = lane & 7, grp = lane >> 3;            // dims 8 sub .. 8 sub + 7; key phase grp (0..3)
+  const uint16_t* qp = p.q + b * p.q_bs + static_cast<int64_t>(row) * p.ldq + p.q_col + h * kD + 8 * sub;
+  const uint16_t* kp = p.k + b * p.k_bs + p.k_col + hk * kD + 8 * sub;
+  const uint16_t* vp = p.v + b * p.v_bs + p.v_col + hk * kD + 8 * sub;
+  float qf[8];
+  {
+    const uint4 u = __ldcg(reinterpret_cast<const uint4*>(qp));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = Op16<BF16>::unpack(w[e]);
+      qf[2 * e] = f.x * p.scale_log2;
+      qf[2 * e + 1] = f.y * p.scale_log2;
+    }
+  }
+  float m_run = -INFINITY, l_run = 0.f;
+  float o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = 0.f;
+  for (int k0 = 0; k0 < p.Nk; k0 += kRowChunk) {
+    const int nk = min(kRowChunk, p.Nk - k0);
+    const int n4 = (nk + 3) >> 2;                       // groups of four keys
+    // ---- scores of this block -> prow[], running block max
+    float mx = -INFINITY;
+#pragma unroll 4
+    for (int i = 0; i < n4; ++i) {
+      const int key = 4 * i + grp;
+      float s = 0.f;
+      if (key < nk) {
+        const uint4 u = __ldcg(reinterpret_cast<const uint4*>(kp + static_cast<int64_t>(k0 + key) * p.ldk));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = Op16<BF16>::unpack(w[e]);
+          s = fmaf(qf[2 * e], f.x, s);
+          s = fmaf(qf[2 * e + 1], f.y, s);
+        }
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (key < nk) {
+        if (sub == 0) prow[key] = s;
+        mx = fmaxf(mx, s);
+      }
+    }
+    mx = warp_max(mx);
+    const float m_new = fmaxf(m_run, mx);
+    const float f = ex2_approx(m_run - m_new);          // 0 on the first block (m_run = -inf)
+    l_run *= f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] *= f;
+    m_run = m_new;
+    __syncwarp();
+    float ls = 0.f;
+    for (int i = lane; i < nk; i += 32) {
+      const float e = ex2_approx(prow[i] - m_new);
+      prow[i] = e;
+      ls += e;
+    }
+    l_run += warp_sum(ls);
+    __syncwarp();
+    // ---- O += P V: lane accumulates its 8 dims over the keys of its phase
+#pragma unroll 4
+    for (int i = 0; i < n4; ++i) {
+      const int key = 4 * i + grp;
+      if (key < nk) {
+        const uint4 u = __ldcg(reinterpret_cast<const uint4*>(vp + static_cast<int64_t>(k0 + key) * p.ldv));
+        const float e = prow[key];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float2 vv = Op16<BF16>::unpack(w[c]);
+          o[2 * c] = fmaf(e, vv.x, o[2 * c]);
+          o[2 * c + 1] = fmaf(e, vv.y, o[2 * c + 1]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // combine the four key phases (lanes l, l + 8, l + 16, l + 24 hold the same dims)
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
+  }
+  if (grp == 0) {
+    const float inv = 1.0f / l_run;
+    uint16_t* og = p.o + b * p.o_bs + static_cast<int64_t>(row) * p.ldo + static_cast<int64_t>(h) * kD + 8 * sub;
+    *reinterpret_cast<uint4*>(og) = make_uint4(Op16<BF16>::pack(o[0] * inv, o[1] * inv), Op16<BF16>::pack(o[2] * inv, o[3] * inv),
+                                                Op16<BF16>::pack(o[4] * inv, o[5] * inv), Op16<BF16>::pack(o[6] * inv, o[7] * inv));
+  }
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(256, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + kQBytes;
-  uint8_t* sV = sK + kStagesK * kKVBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStagesV * kKVBytes);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = k_full + kStagesK;
-  uint64_t* v_full = k_empty + kStagesK;
-  uint64_t* v_empty = v_full + kStagesV;
-  uint64_t* s_full = v_empty + kStagesV;   // [2] MMA -> softmax: S[b] holds Q K_j^T
-  uint64_t* p_ready = s_full + 2;          // [2] softmax -> MMA: S[b] consumed, P[b] written
-  uint64_t* pv_done = p_ready + 2;         // [2] MMA -> softmax: P[b] V retired (P[b] free, O updated)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint8_t* sQ = smem;                                   // [2][16 KB]
+  uint8_t* sK = smem + 2 * kQBytes;                     // [kStagesKV][16 KB]
+  uint8_t* sV = sK + kStagesKV * kKVBytes;
+  float* prow = reinterpret_cast<float*>(sV + kStagesKV * kKVBytes);   // [kRowChunk] row-path scratch
+  uint64_t* bars = reinterpret_cast<uint64_t*>(prow + kRowChunk);
+  uint64_t* q_full = bars;                 // [2]
+  uint64_t* q_empty = bars + 2;            // [2]
+  uint64_t* k_full = bars + 4;             // [kStagesKV]
+  uint64_t* k_empty = k_full + kStagesKV;
+  uint64_t* v_full = k_empty + kStagesKV;
+  uint64_t* v_empty = v_full + kStagesKV;
+  uint64_t* s_full = v_empty + kStagesKV;  // MMA -> softmax: S holds Q K_j^T
+  uint64_t* s_free = s_full + 1;           // softmax -> MMA: S has been read into registers (128 arrivals)
+  uint64_t* p_ready = s_free + 1;          // softmax -> MMA: P written (128 arrivals)
+  uint64_t* p_free = p_ready + 1;          // MMA -> softmax: P V_j retired (P reusable, O up to date)
+  uint64_t* o_done = p_free + 1;           // MMA -> softmax: last P V of the unit retired
+  uint64_t* o_free = o_done + 1;           // softmax -> MMA: O of the previous unit has been read (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+  uint32_t* sm_slot = tmem_slot + 1;       // 0 / 1: which of the SM's two resident CTAs this is
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kQ;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int hk = h / p.group;
   const int n_tiles = (p.Nk + kK - 1) / kK;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < kStagesK; ++i) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
+    for (int i = 0; i < kStagesKV; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
-    }
-    for (int i = 0; i < kStagesV; ++i) {
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], 128);
-      mbar_init(&pv_done[i], 1);
-    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
+    mbar_init(p_ready, 128);
+    mbar_init(p_free, 1);
+    mbar_init(o_done, 1);
+    mbar_init(o_free, 128);
     fence_mbar_init();
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    *sm_slot = p.sm_slots ? static_cast<uint32_t>(atomicAdd(p.sm_slots + smid, 1)) & 1u : 0u;
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, kTmemColsAttn);
@@ -142,74 +280,111 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool odd_cta = *sm_slot != 0;
+  const long long t_start = clock64();
   pdl_launch_dependents();
   pdl_wait();
+
+  // unit u -> (item b, head h, query tile qt); consecutive units share (b, h), i.e. their K / V tiles in L2
+  auto unit_coords = [&](int u, int& b, int& h, int& q0) {
+    const int bh = u / p.n_qt;
+    q0 = (u - bh * p.n_qt) * kQ;
+    b = bh / p.H;
+    h = bh - b * p.H;
+  };
 
   if (warp == 0) {
     if (elect_one()) {
       // ---------------------------------------------------------------- TMA producer
-      mbar_expect_tx(q_full, kQBytes);
-      tma_load_4d(sQ, &tmQ, q_full, p.q_col + h * kD, 0, q0, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int sk = j % kStagesK, sv = j % kStagesV;
-        mbar_wait(&k_empty[sk], ((j / kStagesK) & 1) ^ 1);
-        mbar_expect_tx(&k_full[sk], kKVBytes);
-        tma_load_4d(sK + sk * kKVBytes, &tmK, &k_full[sk], p.k_col + hk * kD, 0, j * kK, b);
-        mbar_wait(&v_empty[sv], ((j / kStagesV) & 1) ^ 1);
-        mbar_expect_tx(&v_full[sv], kKVBytes);
-        tma_load_4d(sV + sv * kKVBytes, &tmV, &v_full[sv], p.v_col + hk * kD, 0, j * kK, b);
+      int g = 0;   // global key-tile counter of this CTA
+      int i = 0;   // local unit counter
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+        int b, h, q0;
+        unit_coords(u, b, h, q0);
+        const int hk = h / p.group;
+        const int qb = i & 1;
+        mbar_wait(&q_empty[qb], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[qb], kQBytes);
+        tma_load_4d(sQ + qb * kQBytes, &tmQ, &q_full[qb], p.q_col + h * kD, 0, q0, b);
+        for (int j = 0; j < n_tiles; ++j, ++g) {
+          const int st = g % kStagesKV;
+          const uint32_t ph = ((g / kStagesKV) & 1) ^ 1;
+          mbar_wait(&k_empty[st], ph);
+          mbar_expect_tx(&k_full[st], kKVBytes);
+          tma_load_4d(sK + st * kKVBytes, &tmK, &k_full[st], p.k_col + hk * kD, 0, j * kK, b);
+          mbar_wait(&v_empty[st], ph);
+          mbar_expect_tx(&v_full[st], kKVBytes);
+          tma_load_4d(sV + st * kKVBytes, &tmV, &v_full[st], p.v_col + hk * kD, 0, j * kK, b);
+        }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      // ------------------------------------------------- MMA issuer 1: S[b] = Q K_j^T, two tiles ahead
-      const uint32_t q_addr = smem_u32(sQ);
-      mbar_wait(q_full, 0);
-      tc_fence_after();
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % kStagesK, sb = j & 1;
-        if (j >= 2) {
-          mbar_wait(&p_ready[sb], ((j - 2) >> 1) & 1);   // S[sb] of tile j-2 has been consumed
-          tc_fence_after();
-        }
-        mbar_wait(&k_full[st], (j / kStagesK) & 1);
+      // ------------------------------------------------- MMA issuer 1: S = Q K_j^T
+      int g = 0, i = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+        const int qb = i & 1;
+        const uint32_t q_addr = smem_u32(sQ + qb * kQBytes);
+        mbar_wait(&q_full[qb], (i >> 1) & 1);
         tc_fence_after();
-        const int nk = min(kK, p.Nk - j * kK);
-        const int n_mma = (nk + 15) & ~15;
-        const uint32_t idesc = make_idesc_f16(kQ, n_mma, BF16);
-        const uint32_t k_addr = smem_u32(sK + st * kKVBytes);
+        for (int j = 0; j < n_tiles; ++j, ++g) {
+          const int st = g % kStagesKV;
+          mbar_wait(&k_full[st], (g / kStagesKV) & 1);
+          if (g >= 1) mbar_wait(s_free, (g - 1) & 1);   // S of the previous tile is in the softmax registers
+          tc_fence_after();
+          const int nk = min(kK, p.Nk - j * kK);
+          const int n_mma = (nk + 15) & ~15;
+          const uint32_t idesc = make_idesc_f16(kQ, n_mma, BF16);
+          const uint32_t k_addr = smem_u32(sK + st * kKVBytes);
 #pragma unroll
-        for (int ks = 0; ks < kD / 16; ++ks)
-          umma_f16_ss(tmem_base + kColS + sb * kK, make_desc_kmajor_sw128(q_addr + ks * 32),
-                      make_desc_kmajor_sw128(k_addr + ks * 32), idesc, ks != 0);
-        umma_commit(&k_empty[st]);   // the K tile is free as soon as these MMAs retire
-        umma_commit(&s_full[sb]);
+          for (int ks = 0; ks < kD / 16; ++ks)
+            umma_f16_ss(tmem_base + kColS, make_desc_kmajor_sw128(q_addr + ks * 32),
+                        make_desc_kmajor_sw128(k_addr + ks * 32), idesc, ks != 0);
+          umma_commit(&k_empty[st]);   // the K tile is free as soon as these MMAs retire
+          umma_commit(s_full);
+        }
+        umma_commit(&q_empty[qb]);     // every Q K^T of this unit has retired: the Q buffer may be refilled
       }
     }
   } else if (warp == 3) {
     if (elect_one()) {
-      // ------------------------------------------------- MMA issuer 2: O += P[b] V_j
+      // ------------------------------------------------- MMA issuer 2: O += P V_j
       constexpr uint32_t idesc_pv = make_idesc_f16(kQ, kD, BF16, /*b_mn_major=*/true);
-      const bool trace = p.dbg != nullptr && blockIdx.x == 3 && blockIdx.y == 11 && blockIdx.z == (gridDim.z / 2);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int sb = j & 1;
-        if (trace) p.dbg[j * 12 + 6] = clock64();
-        mbar_wait(&p_ready[sb], (j >> 1) & 1);   // P[sb] written
-        tc_fence_after();
-        if (trace) p.dbg[j * 12 + 7] = clock64();
-        const int st = j % kStagesV;
-        mbar_wait(&v_full[st], (j / kStagesV) & 1);
-        tc_fence_after();
-        if (trace) p.dbg[j * 12 + 8] = clock64();
-        const int nk = min(kK, p.Nk - j * kK);
-        const int ksteps = (nk + 15) >> 4;
-        const uint32_t v_addr = smem_u32(sV + st * kKVBytes);
-        for (int ks = 0; ks < ksteps; ++ks)
-          umma_f16_ts(tmem_base + kColO, tmem_base + kColP + sb * (kK / 2) + ks * 8,
-                      make_desc_mnmajor_sw128(v_addr + ks * 2048), idesc_pv, (j | ks) != 0);
-        umma_commit(&pv_done[sb]);
-        umma_commit(&v_empty[st]);
-        if (trace) p.dbg[j * 12 + 9] = clock64();
+      int g = 0, i = 0;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+        for (int j = 0; j < n_tiles; ++j, ++g) {
+          const int st = g % kStagesKV;
+          mbar_wait(p_ready, g & 1);
+          mbar_wait(&v_full[st], (g / kStagesKV) & 1);
+          if (j == 0 && i >= 1) mbar_wait(o_free, (i - 1) & 1);   // the previous unit's O has been read out
+          tc_fence_after();
+          const int nk = min(kK, p.Nk - j * kK);
+          const int ksteps = (nk + 15) >> 4;
+          const uint32_t v_addr = smem_u32(sV + st * kKVBytes);
+          if (ksteps == kK / 16) {
+#pragma unroll
+            for (int ks = 0; ks < kK / 16; ++ks)
+              umma_f16_ts(tmem_base + kColO, tmem_base + kColP + ks * 8, make_desc_mnmajor_sw128(v_addr + ks * 2048),
+                          idesc_pv, (j | ks) != 0);
+          } else {
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_f16_ts(tmem_base + kColO, tmem_base + kColP + ks * 8, make_desc_mnmajor_sw128(v_addr + ks * 2048),
+                          idesc_pv, (j | ks) != 0);
+          }
+          umma_commit(p_free);
+          umma_commit(&v_empty[st]);
+          if (j == n_tiles - 1) umma_commit(o_done);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------- ragged query rows on CUDA cores
+    if (p.n_rows > 0) {
+      const int n_tasks = p.batch * p.H * p.n_rows;
+      for (int t = blockIdx.x; t < n_tasks; t += gridDim.x) {
+        const int bh = t / p.n_rows, r = t - bh * p.n_rows;
+        const int b = bh / p.H, h = bh - b * p.H;
+        attn_row_path<BF16>(p, b, h, p.row0 + r, prow, lane);
       }
     }
   } else if (warp >= 4) {
@@ -217,146 +392,186 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int q = warp - 4;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    float m_ref = -INFINITY, l = 0.f;
+    const uint32_t s_addr = t_lane + kColS, p_addr = t_lane + kColP, o_addr = t_lane + kColO;
     const float sc = p.scale_log2;
-    // One pass over S[sb]: P = exp2(S*c - m_ref) -> P[sb]; returns the row sum, tracks the raw max.
-    auto pass_p = [&](int sb, int nk, float& mx_raw) -> float {
-      float sum = 0.f;
-      uint32_t r0[32], r1[32];
-      const uint32_t s_addr = t_lane + kColS + sb * kK, p_addr = t_lane + kColP + sb * (kK / 2);
-      auto do_chunk = [&](int c, const uint32_t (&r)[32]) {
-        uint32_t w[16];
-        if ((c + 1) * 32 <= nk) {
-          const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_ref, -m_ref);
-          uint64_t sum2 = pack2(0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float s0 = __uint_as_float(r[2 * i]), s1 = __uint_as_float(r[2 * i + 1]);
-            mx_raw = fmaxf(fmaxf(mx_raw, s0), s1);
-            float t0, t1;
-            unpack2(ffma2(pack2(s0, s1), sc2, nm2), t0, t1);
-            const float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
-            sum2 = fadd2(sum2, pack2(p0, p1));
-            w[i] = Op16<BF16>::pack(p0, p1);
-          }
-          float a0, a1;
-          unpack2(sum2, a0, a1);
-          sum += a0 + a1;
-        } else {
-          const int lim = nk - c * 32;   // valid columns in this (last) chunk
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float s0 = 2 * i < lim ? __uint_as_float(r[2 * i]) : -INFINITY;
-            const float s1 = 2 * i + 1 < lim ? __uint_as_float(r[2 * i + 1]) : -INFINITY;
-            mx_raw = fmaxf(fmaxf(mx_raw, s0), s1);
-            const float p0 = ex2_approx(fmaf(s0, sc, -m_ref));
-            const float p1 = ex2_approx(fmaf(s1, sc, -m_ref));
-            sum += p0 + p1;
-            w[i] = Op16<BF16>::pack(p0, p1);
-          }
-        }
-        tmem_st_32x16(p_addr + c * 16, w);
-      };
-      tmem_ld_32x32(s_addr, r0);
-      if (nk > 32) tmem_ld_32x32(s_addr + 32, r1);
-      tmem_ld_wait();
-      do_chunk(0, r0);
-      if (nk > 32) do_chunk(1, r1);
-      return sum;
-    };
-    const bool trace = p.dbg != nullptr && blockIdx.x == 3 && blockIdx.y == 11 && blockIdx.z == (gridDim.z / 2) &&
-                       warp == 4 && lane == 0;
-#define SATB_TRACE(idx) do { if (trace) p.dbg[j * 12 + (idx)] = clock64(); } while (0)
-    // a warp whose 32 rows are all beyond Nq (ragged last query tile: 1025 = 8*128 + 1) only keeps
-    // the barrier protocol going; its P rows are never read back through O
-    const bool warp_active = (q0 + q * 32) < p.Nq;
-    for (int j = 0; j < n_tiles; ++j) {
-      const int sb = j & 1;
-      const int nk = min(kK, p.Nk - j * kK);
-      SATB_TRACE(0);
-      mbar_wait(&s_full[sb], (j >> 1) & 1);
-      tc_fence_after();
-      SATB_TRACE(1);
-      if (!warp_active) {
-        if (j >= 2) mbar_wait(&pv_done[sb], ((j - 2) >> 1) & 1);
-        tc_fence_before();
-        mbar_arrive(&p_ready[sb]);
-        continue;
+    const bool trace = p.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
+    // The two resident CTAs of an SM start together and, being identical, would stay in lockstep: both exponentiate
+    // (sharing the SFU) and then both sit in their per-tile bookkeeping with the SFU idle.  The odd one therefore
+    // starts its softmax half a tile period late; the offset persists (neither CTA waits for the other).
+    if (odd_cta)
+      while (clock64() - t_start < p.stagger) {
       }
-      if (j == 0) {
-        // the first tile fixes the reference max before any exponential is taken
-        float mx = -INFINITY;
-        for (int c = 0; c * 32 < nk; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_lane + kColS + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < nk) mx = fmaxf(mx, __uint_as_float(r[i]));
-        }
-        m_ref = mx * sc;
-      }
-      if (j >= 2) {
-        mbar_wait(&pv_done[sb], ((j - 2) >> 1) & 1);   // P[sb] V_{j-2} retired: P[sb] is free
+    int g = 0, i = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+      int b, h, q0;
+      unit_coords(u, b, h, q0);
+      // a warp whose 32 rows are all beyond Nq (partial last query tile) only keeps the barrier protocol going;
+      // its P rows are never read back through O
+      const bool warp_active = (q0 + q * 32) < p.Nq;
+      float m_ref = -INFINITY, l = 0.f;
+      for (int j = 0; j < n_tiles; ++j, ++g) {
+        const int nk = min(kK, p.Nk - j * kK);
+        const int nch = (nk + 31) >> 5;   // 32-column chunks holding real keys
+        if (trace && g < 16) p.dbg[g * 4 + 0] = clock64();
+        mbar_wait(s_full, g & 1);
         tc_fence_after();
-      }
-      SATB_TRACE(2);
-      float mx_raw = -INFINITY;
-      float sum = pass_p(sb, nk, mx_raw);
-      SATB_TRACE(3);
-      // lazy rescale: only when this tile's max exceeds the reference max by more than 2^8
-      const bool need = mx_raw * sc > m_ref + kRescaleThreshold;
-      if (__any_sync(0xffffffffu, need)) {
-        const float m_new = need ? mx_raw * sc : m_ref;
-        const float f = ex2_approx(m_ref - m_new);   // 1 for rows that keep their reference
-        m_ref = m_new;
-        l *= f;
-        if (j > 0) {
-          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // every earlier P V has retired
-          tc_fence_after();
+        if (trace && g < 16) p.dbg[g * 4 + 1] = clock64();
+        if (!warp_active) {
+          tc_fence_before();
+          mbar_arrive(s_free);
+          if (g >= 1) mbar_wait(p_free, (g - 1) & 1);
+          mbar_arrive(p_ready);
+          continue;
+        }
+        uint32_t ra[32], rb[32];
+        // raw max of the valid columns of a chunk
+        auto cmax = [&](int c, const uint32_t (&r)[32]) -> float {
+          float mx = -INFINITY;
+          const int lim = nk - c * 32;
+          if (lim >= 32) {
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(t_lane + kColO + c * 32, r);
-            tmem_ld_wait();
+            for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[e]), __uint_as_float(r[e + 1])));
+          } else {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              uint32_t w[16];
+            for (int e = 0; e < 32; ++e)
+              if (e < lim) mx = fmaxf(mx, __uint_as_float(r[e]));
+          }
+          return mx;
+        };
+        // P chunk = exp2(S c - m_ref) as packed 16-bit pairs in w[]; returns the fp32 row sum of the chunk
+        auto cexp = [&](int c, const uint32_t (&r)[32], uint32_t (&w)[16]) -> float {
+          float sum;
+          const int lim = nk - c * 32;
+          if (lim >= 32) {
+            const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_ref, -m_ref);
+            uint64_t sum2 = pack2(0.f, 0.f);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) w[i] = __float_as_uint(__uint_as_float(r[half * 16 + i]) * f);
-              tmem_st_32x16(t_lane + kColO + c * 32 + half * 16, w);
+            for (int e = 0; e < 16; ++e) {
+              float t0, t1;
+              unpack2(ffma2(pack2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), sc2, nm2), t0, t1);
+              const float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+              sum2 = fadd2(sum2, pack2(p0, p1));
+              w[e] = Op16<BF16>::pack(p0, p1);
+            }
+            float a0, a1;
+            unpack2(sum2, a0, a1);
+            sum = a0 + a1;
+          } else {
+            sum = 0.f;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float s0 = 2 * e < lim ? __uint_as_float(r[2 * e]) : -INFINITY;
+              const float s1 = 2 * e + 1 < lim ? __uint_as_float(r[2 * e + 1]) : -INFINITY;
+              const float p0 = ex2_approx(fmaf(s0, sc, -m_ref));
+              const float p1 = ex2_approx(fmaf(s1, sc, -m_ref));
+              sum += p0 + p1;
+              w[e] = Op16<BF16>::pack(p0, p1);
             }
           }
+          return sum;
+        };
+        // ---- pipelined pass: exponentials of chunks 0,1 (kept in registers) while 2,3 load and while P V of the
+        // previous tile retires -> store them -> release S -> exponentials of chunks 2,3
+        tmem_ld_32x32(s_addr, ra);
+        if (nch > 1) tmem_ld_32x32(s_addr + 32, rb);
+        tmem_ld_wait();
+        float mx_raw = cmax(0, ra);
+        if (nch > 1) mx_raw = fmaxf(mx_raw, cmax(1, rb));
+        // the first tile of a unit fixes the reference max from its first (up to) 64 keys; should a later key of the
+        // tile exceed it by more than 2^8 the lazy-rescale path below recomputes the tile
+        if (j == 0) m_ref = mx_raw * sc;
+        uint32_t w0[16], w1[16];
+        float sum = cexp(0, ra, w0);
+        if (nch > 2) tmem_ld_32x32(s_addr + 64, ra);
+        if (nch > 1) sum += cexp(1, rb, w1);
+        if (nch > 3) tmem_ld_32x32(s_addr + 96, rb);
+        if (g >= 1) {
+          mbar_wait(p_free, (g - 1) & 1);   // P V of the previous tile retired: P may be overwritten, O is quiescent
+          tc_fence_after();
         }
-        float dummy = -INFINITY;
-        sum = pass_p(sb, nk, dummy);   // P again with the new reference max
+        if (trace && g < 16) p.dbg[g * 4 + 2] = clock64();
+        tmem_st_32x16(p_addr, w0);
+        if (nch > 1) tmem_st_32x16(p_addr + 16, w1);
+        if (nch > 2) {
+          tmem_ld_wait();
+          mx_raw = fmaxf(mx_raw, cmax(2, ra));
+          if (nch > 3) mx_raw = fmaxf(mx_raw, cmax(3, rb));
+        }
+        // lazy rescale: only when this tile's max exceeds the reference max by more than 2^8
+        const bool need = mx_raw * sc > m_ref + kRescaleThreshold;
+        if (!__any_sync(0xffffffffu, need)) {
+          tc_fence_before();
+          mbar_arrive(s_free);              // every column of S is in registers: Q K_{j+1}^T may overwrite it
+          if (nch > 2) {
+            sum += cexp(2, ra, w0);
+            tmem_st_32x16(p_addr + 32, w0);
+          }
+          if (nch > 3) {
+            sum += cexp(3, rb, w1);
+            tmem_st_32x16(p_addr + 48, w1);
+          }
+        } else {
+          const float m_new = need ? mx_raw * sc : m_ref;
+          const float f = ex2_approx(m_ref - m_new);   // 1 for rows that keep their reference
+          m_ref = m_new;
+          l *= f;
+          if (j > 0) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t r[32];
+              tmem_ld_32x32(o_addr + c * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                uint32_t w[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) w[e] = __float_as_uint(__uint_as_float(r[half * 16 + e]) * f);
+                tmem_st_32x16(o_addr + c * 32 + half * 16, w);
+              }
+            }
+          }
+          sum = 0.f;                        // P again, all chunks, with the new reference max
+          for (int c = 0; c < nch; ++c) {
+            tmem_ld_32x32(s_addr + c * 32, ra);
+            tmem_ld_wait();
+            sum += cexp(c, ra, w0);
+            tmem_st_32x16(p_addr + c * 16, w0);
+          }
+          tc_fence_before();
+          mbar_arrive(s_free);
+        }
+        l += sum;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_ready);
+        if (trace && g < 16) p.dbg[g * 4 + 3] = clock64();
       }
-      l += sum;
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_ready[sb]);
-      SATB_TRACE(5);
-    }
-#undef SATB_TRACE
-    // epilogue: O / l -> global (128 B per row)
-    mbar_wait(&pv_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
-    tc_fence_after();
-    const float inv = 1.0f / l;
-    const bool valid = (q0 + row) < p.Nq;
-    uint16_t* og = p.o + b * p.o_bs + static_cast<int64_t>(q0 + row) * p.ldo + static_cast<int64_t>(h) * kD;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(t_lane + kColO + c * 32, r);
+      // epilogue of the unit: O / l -> global (128 B per row)
+      mbar_wait(o_done, i & 1);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(o_addr, r0);
+      tmem_ld_32x32(o_addr + 32, r1);
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(o_free);                  // O is in registers: the next unit's first P V may overwrite it
+      const float inv = 1.0f / l;
+      const bool valid = (q0 + row) < p.row0;   // row0 = Nq, or the first row of the CUDA-core path
       if (valid) {
-        uint4* dst = reinterpret_cast<uint4*>(og + c * 32);
+        uint16_t* og = p.o + b * p.o_bs + static_cast<int64_t>(q0 + row) * p.ldo + static_cast<int64_t>(h) * kD;
+        uint4* dst = reinterpret_cast<uint4*>(og);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          dst[i] = make_uint4(Op16<BF16>::pack(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv),
-                              Op16<BF16>::pack(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv),
-                              Op16<BF16>::pack(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv),
-                              Op16<BF16>::pack(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv));
+        for (int e = 0; e < 4; ++e)
+          dst[e] = make_uint4(Op16<BF16>::pack(__uint_as_float(r0[8 * e]) * inv, __uint_as_float(r0[8 * e + 1]) * inv),
+                              Op16<BF16>::pack(__uint_as_float(r0[8 * e + 2]) * inv, __uint_as_float(r0[8 * e + 3]) * inv),
+                              Op16<BF16>::pack(__uint_as_float(r0[8 * e + 4]) * inv, __uint_as_float(r0[8 * e + 5]) * inv),
+                              Op16<BF16>::pack(__uint_as_float(r0[8 * e + 6]) * inv, __uint_as_float(r0[8 * e + 7]) * inv));
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          dst[4 + e] = make_uint4(Op16<BF16>::pack(__uint_as_float(r1[8 * e]) * inv, __uint_as_float(r1[8 * e + 1]) * inv),
+                                  Op16<BF16>::pack(__uint_as_float(r1[8 * e + 2]) * inv, __uint_as_float(r1[8 * e + 3]) * inv),
+                                  Op16<BF16>::pack(__uint_as_float(r1[8 * e + 4]) * inv, __uint_as_float(r1[8 * e + 5]) * inv),
+                                  Op16<BF16>::pack(__uint_as_float(r1[8 * e + 6]) * inv, __uint_as_float(r1[8 * e + 7]) * inv));
       }
     }
   }
@@ -386,6 +601,8 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
   SATB_REQUIRE(H % H_kv == 0, "num_heads must be a multiple of kv heads");
   SATB_REQUIRE(Nk >= 1 && Nq >= 1, "empty attention problem");
   SATB_REQUIRE(ldo % 8 == 0, "attention output stride must be 16B aligned");
+  SATB_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && q_col % 8 == 0 && k_col % 8 == 0 && v_col % 8 == 0,
+               "attention operand strides / column offsets must be 16B aligned");
   CUtensorMap tq, tk, tv;
   SATB_PROPAGATE(make_tmap_rows(&tq, q, q_cols, Nq, batch, ldq, q_bs, kQ));
   SATB_PROPAGATE(make_tmap_rows(&tk, k, k_cols, Nk, batch, ldk, k_bs, kK));
@@ -393,19 +610,60 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
   AttnTcArgs a;
   a.o = static_cast<uint16_t*>(o);
   a.ldo = ldo; a.o_bs = o_bs;
-  a.Nq = Nq; a.Nk = Nk; a.group = H / H_kv;
+  a.Nq = Nq; a.Nk = Nk; a.group = H / H_kv; a.H = H; a.batch = batch;
   a.q_col = q_col; a.k_col = k_col; a.v_col = v_col;
+  // query rows: full 128-row tiles on the tensor cores; a remainder of <= kRowPathMax rows on CUDA cores, a larger
+  // remainder as one more (partial) tensor-core tile
+  const int rem = Nq % kQ;
+  const bool row_path = rem != 0 && rem <= kRowPathMax;
+  a.n_qt = Nq / kQ + ((rem != 0 && !row_path) ? 1 : 0);
+  a.n_units = batch * H * a.n_qt;
+  a.row0 = row_path ? Nq - rem : Nq;
+  a.n_rows = row_path ? rem : 0;
+  a.q = static_cast<const uint16_t*>(q); a.k = static_cast<const uint16_t*>(k); a.v = static_cast<const uint16_t*>(v);
+  a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.q_bs = q_bs; a.k_bs = k_bs; a.v_bs = v_bs;
   a.scale_log2 = (1.0f / sqrtf(64.0f)) * 1.4426950408889634f;
   a.dbg = dbg;
-  dim3 grid(ceil_div(Nq, kQ), H, batch);
+  {
+    static int* slots[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!slots[dev]) {   // once per device (first call = warm-up, never inside a graph capture)
+      SATB_CHECK_CUDA(cudaMalloc(&slots[dev], 1024 * sizeof(int)));
+      SATB_CHECK_CUDA(cudaMemset(slots[dev], 0, 1024 * sizeof(int)));
+    }
+    a.sm_slots = slots[dev];
+    static int stagger = -1;
+    if (stagger < 0) {
+      const char* e = getenv("SATB_ATTN_STAGGER");   // cycles; tuning / A-B only
+      stagger = e ? atoi(e) : 1100;
+    }
+    a.stagger = stagger;
+  }
+  const int row_tasks = batch * H * a.n_rows;
+  int grid = a.n_units > row_tasks ? a.n_units : row_tasks;
+  const int slots = 2 * device_sm_count();
+  if (grid > slots) grid = slots;
+  if (grid <= 0) return 0;
+  static PerDeviceOnce attr16, attrbf;
+  auto prepare = [&](auto kern) -> int {
+    SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    // two CTAs per SM need 2 x 102 KB: ask for the largest shared-memory carveout
+    SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (getenv("SATB_ATTN_DEBUG")) {
+      int nb = -1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, kAttnSmem);
+      fprintf(stderr, "[satb] attention: %d resident CTAs per SM (smem %d B per CTA)\n", nb, kAttnSmem);
+    }
+    return 0;
+  };
   if (bf16) {
-    static bool set = false;
-    if (!set) { SATB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem)); set = true; }
-    SATB_CHECK_CUDA(launch_pdl(attn_tc_kernel<true>, grid, dim3(256), kAttnSmem, stream, tq, tk, tv, a));
+    if (attrbf.first()) SATB_PROPAGATE(prepare(attn_tc_kernel<true>));
+    SATB_CHECK_CUDA(launch_pdl(attn_tc_kernel<true>, dim3(grid), dim3(256), kAttnSmem, stream, tq, tk, tv, a));
   } else {
-    static bool set = false;
-    if (!set) { SATB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem)); set = true; }
-    SATB_CHECK_CUDA(launch_pdl(attn_tc_kernel<false>, grid, dim3(256), kAttnSmem, stream, tq, tk, tv, a));
+    if (attr16.first()) SATB_PROPAGATE(prepare(attn_tc_kernel<false>));
+    SATB_CHECK_CUDA(launch_pdl(attn_tc_kernel<false>, dim3(grid), dim3(256), kAttnSmem, stream, tq, tk, tv, a));
   }
   count_launch();
   SATB_CHECK_CUDA(cudaGetLastError());

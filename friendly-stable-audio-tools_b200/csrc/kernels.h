@@ -14,6 +14,7 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
 bool conv_halo_enabled();     // SATB_CONV_HALO=off: generic 7-tap loads for the final conv (A/B debugging)
 bool resunit_use_fused();      // SATB_RESUNIT=unfused runs the 128-channel ResidualUnits as two GEMM launches (A/B debugging)
 bool gemm_use_2cta();          // SATB_GEMM=1cta disables the CTA-pair GEMM (A/B debugging)
+bool raw_stream_16bit();       // SATB_RAW=fp32 keeps the Oobleck skip stream in fp32 (A/B debugging)
 
 // ---- elementwise.cu
 // LayerNorm over the last dim (eps 1e-5), optional adaLN modulation y*(1+scale)+shift, 16-bit output.

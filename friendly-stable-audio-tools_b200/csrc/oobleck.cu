@@ -119,8 +119,9 @@ __global__ void __launch_bounds__(256) ncl_to_nlc16_kernel(const float* __restri
 template <bool BF16>
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ audio, const float* __restrict__ w,
                                                       const float* __restrict__ bias, const float* __restrict__ sn_a,
-                                                      const float* __restrict__ sn_ib, float* __restrict__ raw,
-                                                      uint16_t* __restrict__ s16, int Cin, int C, int64_t T, int kk) {
+                                                      const float* __restrict__ sn_ib, void* __restrict__ raw,
+                                                      uint16_t* __restrict__ s16, int Cin, int C, int64_t T, int kk,
+                                                      int raw16) {
   constexpr int kTile = 64;
   extern __shared__ float sm_in[];  // [Cin][kTile + kk - 1]
   const int b = blockIdx.y;
@@ -144,7 +145,12 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
       for (int ci = 0; ci < Cin; ++ci)
         for (int t = 0; t < kk; ++t) acc = fmaf(wr[ci * kk + t], sm_in[ci * span + j + t], acc);
       const size_t o = (static_cast<size_t>(b) * T + l) * C + co;
-      raw[o] = acc;
+      if (raw16) {
+        typename Op16<BF16>::T r = Op16<BF16>::from_float(acc);
+        static_cast<uint16_t*>(raw)[o] = *reinterpret_cast<uint16_t*>(&r);
+      } else {
+        static_cast<float*>(raw)[o] = acc;
+      }
       typename Op16<BF16>::T h = Op16<BF16>::from_float(snake_fast(acc, a, ib));
       s16[o] = *reinterpret_cast<uint16_t*>(&h);
     }
@@ -174,6 +180,7 @@ using namespace satb;
 struct SatbOobleck {
   SatbOobleckConfig cfg;
   bool bf16 = false;
+  int raw16 = 0;                   // 1: the raw skip stream is carried in the 16-bit operand type (fp16 mode), 0: fp32
   std::vector<int> chans;          // c_mults[i] * channels, i = 0..n (c_mults prepended with 1)
   std::map<std::string, std::pair<float*, long long>> raw;   // state-dict entries (device fp32)
   std::vector<void*> owned;
@@ -353,14 +360,14 @@ int run_conv_gemm(SatbOobleck* h, const ConvW& cw, const void* in16, int B, int 
 // Out: y = x + conv1(snake2(conv7(.))) as fp32 in raw (if keep_raw) and snake_next(y) as 16-bit in sA;
 // sT is scratch (the two pointers are swapped when the fused kernel wrote its output there).
 template <bool BF16>
-int residual_unit(SatbOobleck* h, const std::string& pfx, int C, int B, int L, int dil, float* raw, void*& sA, void*& sT,
+int residual_unit(SatbOobleck* h, const std::string& pfx, int C, int B, int L, int dil, void* raw, void*& sA, void*& sT,
                   const SnakeW* next_snake, bool keep_raw, cudaStream_t st) {
   const ConvW& c7 = h->convs.at(pfx + "layers.1.");
   const ConvW& c1 = h->convs.at(pfx + "layers.3.");
   const SnakeW& s2 = h->snakes.at(pfx + "layers.2.");
   typedef EpiConv<BF16> E;
   typename E::Params e1{c1.bias, raw, keep_raw ? raw : nullptr, sA, next_snake ? next_snake->a : nullptr,
-                        next_snake ? next_snake->ib : nullptr, C, L, 1, 0};
+                        next_snake ? next_snake->ib : nullptr, C, L, 1, 0, h->raw16};
   if (C == ResUnitCfg::kC && c7.k == ResUnitCfg::kTaps && dil <= ResUnitCfg::kMaxDil && L >= 512 && gemm_use_2cta() &&
       resunit_use_fused()) {
     // one kernel: conv7 -> snake2 -> conv1 -> + skip; reads sA (with a halo), so it must write elsewhere
@@ -389,7 +396,7 @@ int residual_unit(SatbOobleck* h, const std::string& pfx, int C, int B, int L, i
     return 0;
   }
   // conv7(dil) on sA -> snake2 -> sT ; conv1 on sT -> + x -> raw, snake_next -> sA
-  typename E::Params e7{c7.bias, nullptr, nullptr, sT, s2.a, s2.ib, C, L, 1, 0};
+  typename E::Params e7{c7.bias, nullptr, nullptr, sT, s2.a, s2.ib, C, L, 1, 0, h->raw16};
   SATB_PROPAGATE((run_conv_gemm<E, BF16>(h, c7, sA, B, L, 0, dil, 1, e7, st)));
   SATB_PROPAGATE((run_conv_gemm<E, BF16>(h, c1, sT, B, L, 0, 1, 1, e1, st)));
   return 0;
@@ -412,7 +419,7 @@ int decode_impl(SatbOobleck* h, const float* z, float* audio, int B, int L, cuda
   SATB_PROPAGATE(h->ensure(&h->buf_raw, &h->cap_raw, max_elems * 4));
   SATB_PROPAGATE(h->ensure(&h->buf_a, &h->cap_a, max_elems * 2));
   SATB_PROPAGATE(h->ensure(&h->buf_b, &h->cap_b, max_elems * 2));
-  float* raw = static_cast<float*>(h->buf_raw);
+  void* raw = h->buf_raw;
   void* sA = h->buf_a;
   void* sB = h->buf_b;
   typedef EpiConv<BF16> E;
@@ -426,7 +433,7 @@ int decode_impl(SatbOobleck* h, const float* z, float* audio, int B, int L, cuda
   {
     const ConvW& c0 = h->convs.at("layers.0.");
     const SnakeW& sn = h->snakes.at("layers.1.layers.0.");
-    typename E::Params ep{c0.bias, nullptr, nullptr, sA, sn.a, sn.ib, c0.cout, L, 1, 0};
+    typename E::Params ep{c0.bias, nullptr, nullptr, sA, sn.a, sn.ib, c0.cout, L, 1, 0, h->raw16};
     SATB_PROPAGATE((run_conv_gemm<E, BF16>(h, c0, sB, B, L, 0, 1, 1, ep, st)));
   }
   int64_t Lc = L;
@@ -438,7 +445,7 @@ int decode_impl(SatbOobleck* h, const float* z, float* audio, int B, int L, cuda
     const int64_t Lo = Lc * s;
     SATB_REQUIRE(Lo < (int64_t(1) << 31) && static_cast<int64_t>(B) * Lo * cout < (int64_t(1) << 40), "decoder: sequence too long");
     // transposed conv reads sA [B, Lc, cin], writes raw + snake(ru0) into sB
-    typename E::Params et{ct.bias, nullptr, raw, sB, s_ru0.a, s_ru0.ib, cout, static_cast<int>(Lo), s, (s + 1) / 2};
+    typename E::Params et{ct.bias, nullptr, raw, sB, s_ru0.a, s_ru0.ib, cout, static_cast<int>(Lo), s, (s + 1) / 2, h->raw16};
     SATB_PROPAGATE((run_conv_gemm<E, BF16>(h, ct, sA, B, static_cast<int>(Lc), 1, 1, s, et, st)));
     std::swap(sA, sB);  // sA now holds the residual units' input
     for (int j = 0; j < 3; ++j) {
@@ -497,7 +504,7 @@ int encode_impl(SatbOobleck* h, const float* audio, float* latents, int B, int64
   SATB_PROPAGATE(h->ensure(&h->buf_raw, &h->cap_raw, max_elems * 4));
   SATB_PROPAGATE(h->ensure(&h->buf_a, &h->cap_a, max_elems * 2));
   SATB_PROPAGATE(h->ensure(&h->buf_b, &h->cap_b, max_elems * 2));
-  float* raw = static_cast<float*>(h->buf_raw);
+  void* raw = h->buf_raw;
   void* sA = h->buf_a;
   void* sB = h->buf_b;
   typedef EpiConv<BF16> E;
@@ -509,7 +516,7 @@ int encode_impl(SatbOobleck* h, const float* audio, float* latents, int B, int64
     const size_t smem = static_cast<size_t>(c0.cin) * (64 + c0.k - 1) * 4;
     dim3 grid(static_cast<unsigned>(ceil_div64(T, 64)), B);
     conv_in_kernel<BF16><<<grid, 256, smem, st>>>(audio, c0.w32, c0.bias, sn.a, sn.ib, raw, static_cast<uint16_t*>(sA),
-                                                   c0.cin, c0.cout, T, c0.k);
+                                                   c0.cin, c0.cout, T, c0.k, h->raw16);
     count_launch();
   }
   int64_t Lc = T;
@@ -528,7 +535,7 @@ int encode_impl(SatbOobleck* h, const float* audio, float* latents, int B, int64
     const int64_t Lo = Lc / s;
     const SnakeW* nx = b < n ? &h->snakes.at("layers." + std::to_string(b + 1) + ".layers.0.layers.0.")
                              : &h->snakes.at("layers." + std::to_string(n + 1) + ".");
-    typename E::Params ep{cs.bias, nullptr, b < n ? raw : nullptr, sB, nx->a, nx->ib, cs.cout, static_cast<int>(Lo), 1, 0};
+    typename E::Params ep{cs.bias, nullptr, b < n ? raw : nullptr, sB, nx->a, nx->ib, cs.cout, static_cast<int>(Lo), 1, 0, h->raw16};
     SATB_PROPAGATE((run_conv_gemm<E, BF16>(h, cs, sA, B, static_cast<int>(Lc), 2, 1, s, ep, st)));
     std::swap(sA, sB);
     Lc = Lo;
@@ -555,6 +562,10 @@ int satb_oobleck_create(const SatbOobleckConfig* cfg, SatbOobleck** out) {
   SatbOobleck* h = new SatbOobleck();
   h->cfg = *cfg;
   h->bf16 = cfg->operand_dtype == 1;
+  // fp16 operands: the un-activated skip stream is carried in fp16 as well (8 instead of 12 bytes per element and
+  // channel through a fused ResidualUnit; measured +23 % on the fp16-operand error floor, tests/test_gpu_baseline_size).
+  // bf16 (8 mantissa bits) keeps the fp32 stream.  SATB_RAW=fp32 restores fp32 for A/B measurements.
+  h->raw16 = (!h->bf16 && raw_stream_16bit()) ? 1 : 0;
   h->chans.push_back(cfg->channels);
   for (int i = 0; i < cfg->n_stages; ++i) h->chans.push_back(cfg->c_mults[i] * cfg->channels);
   *out = h;

@@ -25,6 +25,15 @@ bool gemm_use_2cta() {
   return v == 1;
 }
 
+bool raw_stream_16bit() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SATB_RAW");
+    v = (e && std::string(e) == "fp32") ? 0 : 1;
+  }
+  return v == 1;
+}
+
 bool conv_halo_enabled() {
   static int v = -1;
   if (v < 0) {

@@ -7,31 +7,20 @@ The CSV comes from
 dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --kernel-name-base demangled \
       -k regex:satb -s <skip> -c <count> --csv --log-file <csv> python tests/prof_step.py oobleck 1024
 (durations under ncu are cold-cache and serialised: use them for shares, not as bench values).
-Algorithmic bytes follow DESIGN.md: 16-bit activated copies, fp32 raw skip stream.
+Algorithmic bytes: profiles/tools/decoder_bytes.py (16-bit activated copies; raw skip stream 2 B, or 4 B with --raw32).
 """
 import collections
 import csv
 import sys
 
 
-def layers(L, fused128=True):
-    """(name, flops, algorithmic bytes) in launch order for the SA-Open-1.0 decoder.  With fused128 the
-    128- and 256-channel ResidualUnits are one launch each (resunit[256]_tcgen05_2cta_kernel)."""
-    out = [("ncl->nlc16", 0, 64 * L * 6)]
-    out.append(("conv_in k7 64->2048", 2 * L * 64 * 2048 * 7, L * (64 * 2 + 2048 * 6)))
-    cin = 2048
-    for s, cout in zip((8, 8, 4, 4, 2), (1024, 512, 256, 128, 128)):
-        lo = L * s
-        out.append((f"convT s{s} {cin}->{cout}", 2 * L * cin * cout * 2 * s, L * cin * 2 + lo * cout * 6))
-        for d in (1, 3, 9):
-            if fused128 and cout in (128, 256):
-                out.append((f"  resunit d{d} {cout} (fused)", 2 * lo * cout * cout * 8, lo * cout * (2 + 4 + 4 + 2)))
-                continue
-            out.append((f"  conv7 d{d} {cout}", 2 * lo * cout * cout * 7, lo * cout * 4))
-            out.append((f"  conv1+skip {cout}", 2 * lo * cout * cout, lo * cout * (2 + 4 + 4 + 2)))
-        cin, L = cout, lo
-    out.append(("conv_out k7 128->2", 2 * L * 128 * 2 * 7, L * (128 * 2 + 2 * 4)))
-    return out
+import os
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from decoder_bytes import layers as _layers      # the byte model bench.py uses
+
+
+def layers(L, fused128=True, raw_bytes=2):
+    return _layers(L, raw_bytes, fused128)
 
 
 def main():
@@ -45,7 +34,7 @@ def main():
         d[r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
         d["unit:" + r["Metric Name"]] = r["Metric Unit"]
     ids = [i for i in by if i >= first]
-    spec = layers(L, fused128="--unfused" not in sys.argv)
+    spec = layers(L, fused128="--unfused" not in sys.argv, raw_bytes=4 if "--raw32" in sys.argv else 2)
     tot_t = tot_f = tot_b = tot_d = 0.0
     print(f"{'layer':28s} {'us':>8s} {'TF/s':>7s} {'alg GB/s':>9s} {'dram GB/s':>9s} {'tensor%':>7s}")
     for (name, fl, by_alg), i in zip(spec, ids):

@@ -68,16 +68,25 @@ def test_decode_audio_chunked_vs_reference_golden():
 def test_reconstruct_audio_chunked_vs_reference_golden():
     """reconstruct_audio(chunked, chunk 7, overlap 1) against the real reference's output: the VAE noise the
     reference drew from the CPU generator (seed stored in the golden) is replayed into the native run by
-    replacing torch.randn_like (models/bottleneck.py:50) with draws from the same CPU stream."""
+    replacing torch.randn_like (models/bottleneck.py:50) with draws from the same CPU stream.  Encoder, VAE sample
+    and decoder in sequence: the gate is 2x the fp16-operand floor of the same pipeline on the oracle."""
+    from oracle import oobleck_oracle as oo
     from oracle.make_golden import cpu_stream_randn_like
     g, ae = _build()
-    a = torch.from_numpy(g["a"]).cuda()
+    dcfg, ecfg = json.loads(str(g["dec_cfg"])), json.loads(str(g["enc_cfg"]))
+    a = torch.from_numpy(g["a"])
+    gold = torch.from_numpy(g["rec"])
     torch.manual_seed(int(g["rec_seed"]))
     with cpu_stream_randn_like():
-        rec = ae.reconstruct_audio(a, chunked=True, chunk_size=7, overlap=1, max_batch_size=3)
+        rec = ae.reconstruct_audio(a.cuda(), chunked=True, chunk_size=7, overlap=1, max_batch_size=3)
+    dsd = {k: v.detach().cpu() for k, v in ae.decoder.state_dict().items()}
+    esd = {k: v.detach().cpu() for k, v in ae.encoder.state_dict().items()}
+    torch.manual_seed(int(g["rec_seed"]))
+    with cpu_stream_randn_like() as draw, oo.operand_rounding(torch.float16):
+        floor = rel_l2(oo.reconstruct_audio_chunked(a, esd, dsd, ecfg, dcfg, 7, 1, 3, draw), gold)
     assert rec.shape == tuple(g["rec"].shape)
-    err = rel_l2(rec.cpu(), torch.from_numpy(g["rec"]))
-    assert err < 2 * TOL["fp16"], err          # encoder and decoder in sequence
+    err = rel_l2(rec.cpu(), gold)
+    assert err < 2.0 * floor and err < 2e-2, (err, floor)
 
 
 def test_decoder_batch_and_iterate_batch_agree():
