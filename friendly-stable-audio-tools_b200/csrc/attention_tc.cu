@@ -1,10 +1,10 @@
 // tcgen05 attention forward, head dim 64, no mask, non-causal, optional GQA:
 //   O = softmax(Q K^T / sqrt(64)) V      (reference models/transformer.py:496-536)
 //
-// Persistent kernel, two CTAs per SM (2 x 256 TMEM columns, 2 x 101 KB shared memory).  A work unit is 128 query
+// Persistent kernel, two CTAs per SM (2 x 256 TMEM columns, 2 x 85 KB shared memory).  A work unit is 128 query
 // rows of one (batch item, head); CTA c processes units c, c + grid, ... without re-initialising anything.  Keys
 // are processed in tiles of 128:
-//   warp 0 (one thread)  TMA producer: Q of the next unit (double-buffered), K / V tiles (2-stage rings)
+//   warp 0 (one thread)  TMA producer: Q of the unit, K / V tiles (2-stage rings)
 //   warp 1 (one thread)  S = Q K_j^T -> TMEM (tcgen05.mma, smem operands) as soon as S has been read out
 //   warp 3 (one thread)  O += P V_j (A = P from TMEM, B = V tile addressed MN-major)
 //   warps 4-7            one query row per thread: P = exp2(S c - m_ref) -> TMEM as packed 16-bit pairs, row sum
@@ -42,8 +42,9 @@ constexpr int kStagesKV = 2;
 constexpr int kQBytes = kQ * kD * 2;                         // 16 KB
 constexpr int kKVBytes = kK * kD * 2;                        // 16 KB
 constexpr int kRowChunk = 1024;                              // keys per block of the CUDA-core row path
+constexpr int kRowBatch = 16;                                // independent 16-byte loads in flight per lane (row path)
 constexpr int kRowPathMax = 2;                               // Nq % 128 <= this: those rows take the row path
-constexpr int kAttnSmem = 2 * kQBytes + 2 * kStagesKV * kKVBytes + kRowChunk * 4 + 256 + 1024;
+constexpr int kAttnSmem = kQBytes + 2 * kStagesKV * kKVBytes + kRowChunk * 4 + 256 + 1024;   // 85.25 KB: two CTAs per SM
 constexpr int kTmemColsAttn = 256;
 constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;
 constexpr float kRescaleThreshold = 8.0f;                    // log2 units
@@ -79,6 +80,13 @@ __device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t smem_addr) 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// same instruction, but volatile: the compiler keeps a run of these in program order (see cexp below)
+__device__ __forceinline__ float ex2_ordered(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
@@ -146,28 +154,36 @@ __device__ void attn_row_path(const AttnTcArgs& p, int b, int h, int row, float*
   for (int k0 = 0; k0 < p.Nk; k0 += kRowChunk) {
     const int nk = min(kRowChunk, p.Nk - k0);
     const int n4 = (nk + 3) >> 2;                       // groups of four keys
-    // ---- scores of this block -> prow[], running block max
+    // ---- scores of this block -> prow[], running block max.  Loads are issued in explicit batches of kRowBatch
+    // independent 16-byte loads per lane (the compiler will not hoist a global load above the shared-memory store
+    // of the previous iteration, which would serialise one L2 round trip per group of four keys).
     float mx = -INFINITY;
-#pragma unroll 4
-    for (int i = 0; i < n4; ++i) {
-      const int key = 4 * i + grp;
-      float s = 0.f;
-      if (key < nk) {
-        const uint4 u = __ldcg(reinterpret_cast<const uint4*>(kp + static_cast<int64_t>(k0 + key) * p.ldk));
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int i0 = 0; i0 < n4; i0 += kRowBatch) {
+      uint4 u[kRowBatch];
+#pragma unroll
+      for (int jj = 0; jj < kRowBatch; ++jj) {
+        const int key = 4 * (i0 + jj) + grp;
+        u[jj] = key < nk ? __ldcg(reinterpret_cast<const uint4*>(kp + static_cast<int64_t>(k0 + key) * p.ldk))
+                         : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int jj = 0; jj < kRowBatch; ++jj) {
+        const int key = 4 * (i0 + jj) + grp;
+        const uint32_t w[4] = {u[jj].x, u[jj].y, u[jj].z, u[jj].w};
+        float s = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 f = Op16<BF16>::unpack(w[e]);
           s = fmaf(qf[2 * e], f.x, s);
           s = fmaf(qf[2 * e + 1], f.y, s);
         }
-      }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      if (key < nk) {
-        if (sub == 0) prow[key] = s;
-        mx = fmaxf(mx, s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (key < nk) {
+          if (sub == 0) prow[key] = s;
+          mx = fmaxf(mx, s);
+        }
       }
     }
     mx = warp_max(mx);
@@ -186,14 +202,20 @@ __device__ void attn_row_path(const AttnTcArgs& p, int b, int h, int row, float*
     }
     l_run += warp_sum(ls);
     __syncwarp();
-    // ---- O += P V: lane accumulates its 8 dims over the keys of its phase
-#pragma unroll 4
-    for (int i = 0; i < n4; ++i) {
-      const int key = 4 * i + grp;
-      if (key < nk) {
-        const uint4 u = __ldcg(reinterpret_cast<const uint4*>(vp + static_cast<int64_t>(k0 + key) * p.ldv));
-        const float e = prow[key];
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    // ---- O += P V: lane accumulates its 8 dims over the keys of its phase (same batching)
+    for (int i0 = 0; i0 < n4; i0 += kRowBatch) {
+      uint4 u[kRowBatch];
+#pragma unroll
+      for (int jj = 0; jj < kRowBatch; ++jj) {
+        const int key = 4 * (i0 + jj) + grp;
+        u[jj] = key < nk ? __ldcg(reinterpret_cast<const uint4*>(vp + static_cast<int64_t>(k0 + key) * p.ldv))
+                         : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int jj = 0; jj < kRowBatch; ++jj) {
+        const int key = 4 * (i0 + jj) + grp;
+        const float e = key < nk ? prow[key] : 0.f;
+        const uint32_t w[4] = {u[jj].x, u[jj].y, u[jj].z, u[jj].w};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const float2 vv = Op16<BF16>::unpack(w[c]);
@@ -224,13 +246,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmV, const AttnTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                   // [2][16 KB]
-  uint8_t* sK = smem + 2 * kQBytes;                     // [kStagesKV][16 KB]
+  uint8_t* sQ = smem;                                   // [16 KB] (single: the last Q K^T of a unit is issued a whole
+                                                        // tile before the unit ends, which is the time the next Q has to arrive)
+  uint8_t* sK = smem + kQBytes;                         // [kStagesKV][16 KB]
   uint8_t* sV = sK + kStagesKV * kKVBytes;
   float* prow = reinterpret_cast<float*>(sV + kStagesKV * kKVBytes);   // [kRowChunk] row-path scratch
   uint64_t* bars = reinterpret_cast<uint64_t*>(prow + kRowChunk);
-  uint64_t* q_full = bars;                 // [2]
-  uint64_t* q_empty = bars + 2;            // [2]
+  uint64_t* q_full = bars;                 // [1] (+1 unused)
+  uint64_t* q_empty = bars + 2;            // [1] (+1 unused)
   uint64_t* k_full = bars + 4;             // [kStagesKV]
   uint64_t* k_empty = k_full + kStagesKV;
   uint64_t* v_full = k_empty + kStagesKV;
@@ -302,10 +325,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         int b, h, q0;
         unit_coords(u, b, h, q0);
         const int hk = h / p.group;
-        const int qb = i & 1;
-        mbar_wait(&q_empty[qb], ((i >> 1) & 1) ^ 1);
-        mbar_expect_tx(&q_full[qb], kQBytes);
-        tma_load_4d(sQ + qb * kQBytes, &tmQ, &q_full[qb], p.q_col + h * kD, 0, q0, b);
+        mbar_wait(&q_empty[0], (i & 1) ^ 1);
+        mbar_expect_tx(&q_full[0], kQBytes);
+        tma_load_4d(sQ, &tmQ, &q_full[0], p.q_col + h * kD, 0, q0, b);
         for (int j = 0; j < n_tiles; ++j, ++g) {
           const int st = g % kStagesKV;
           const uint32_t ph = ((g / kStagesKV) & 1) ^ 1;
@@ -323,9 +345,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // ------------------------------------------------- MMA issuer 1: S = Q K_j^T
       int g = 0, i = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
-        const int qb = i & 1;
-        const uint32_t q_addr = smem_u32(sQ + qb * kQBytes);
-        mbar_wait(&q_full[qb], (i >> 1) & 1);
+        const uint32_t q_addr = smem_u32(sQ);
+        mbar_wait(&q_full[0], i & 1);
         tc_fence_after();
         for (int j = 0; j < n_tiles; ++j, ++g) {
           const int st = g % kStagesKV;
@@ -343,7 +364,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           umma_commit(&k_empty[st]);   // the K tile is free as soon as these MMAs retire
           umma_commit(s_full);
         }
-        umma_commit(&q_empty[qb]);     // every Q K^T of this unit has retired: the Q buffer may be refilled
+        umma_commit(&q_empty[0]);      // every Q K^T of this unit has retired: the Q buffer may be refilled
       }
     }
   } else if (warp == 3) {
@@ -443,18 +464,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           float sum;
           const int lim = nk - c * 32;
           if (lim >= 32) {
+            // three phases, so that the 32 MUFU.EX2 are issued back to back and none of their consumers waits on a
+            // result that is still in the SFU pipeline (a lone warp per scheduler cannot hide that latency)
             const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_ref, -m_ref);
-            uint64_t sum2 = pack2(0.f, 0.f);
+            float t[32];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              float t0, t1;
-              unpack2(ffma2(pack2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), sc2, nm2), t0, t1);
-              const float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
-              sum2 = fadd2(sum2, pack2(p0, p1));
-              w[e] = Op16<BF16>::pack(p0, p1);
+            for (int e = 0; e < 16; ++e)
+              unpack2(ffma2(pack2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), sc2, nm2), t[2 * e], t[2 * e + 1]);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) t[e] = ex2_ordered(t[e]);
+            uint64_t sum2a = pack2(0.f, 0.f), sum2b = pack2(0.f, 0.f);
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+              sum2a = fadd2(sum2a, pack2(t[2 * e], t[2 * e + 1]));
+              sum2b = fadd2(sum2b, pack2(t[2 * e + 2], t[2 * e + 3]));
+              w[e] = Op16<BF16>::pack(t[2 * e], t[2 * e + 1]);
+              w[e + 1] = Op16<BF16>::pack(t[2 * e + 2], t[2 * e + 3]);
             }
             float a0, a1;
-            unpack2(sum2, a0, a1);
+            unpack2(fadd2(sum2a, sum2b), a0, a1);
             sum = a0 + a1;
           } else {
             sum = 0.f;
@@ -652,9 +680,16 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
     // two CTAs per SM need 2 x 102 KB: ask for the largest shared-memory carveout
     SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (getenv("SATB_ATTN_DEBUG")) {
-      int nb = -1;
+      int nb = -1, dev = 0, sm_smem = 0, rsv = 0, regs = 0;
+      cudaGetDevice(&dev);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, kAttnSmem);
-      fprintf(stderr, "[satb] attention: %d resident CTAs per SM (smem %d B per CTA)\n", nb, kAttnSmem);
+      cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+      cudaDeviceGetAttribute(&rsv, cudaDevAttrReservedSharedMemoryPerBlock, dev);
+      cudaDeviceGetAttribute(&regs, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, kern);
+      fprintf(stderr, "[satb] attention: %d resident CTAs per SM (dyn smem %d B + static %zu B per CTA, %d regs/thread; SM: "
+              "%d B smem, %d B reserved per block, %d regs)\n", nb, kAttnSmem, fa.sharedSizeBytes, fa.numRegs, sm_smem, rsv, regs);
     }
     return 0;
   };

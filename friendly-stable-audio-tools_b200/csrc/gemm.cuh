@@ -851,9 +851,10 @@ struct EpiConv {
       rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (ok && p.resid) {
         if (p.raw16) {
+          // keep the loaded BITS (converted in finish()): touching the value here would wait for the load and
+          // defeat the point of requesting the skip rows early
           const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(p.resid) + idx);
-          const float2 lo = Op16<BF16>::unpack(u.x), hi = Op16<BF16>::unpack(u.y);
-          rs[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+          rs[i] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), 0.f, 0.f);
         } else {
           rs[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.resid) + idx);
         }
@@ -886,7 +887,15 @@ struct EpiConv {
       size_t idx;
       if (seg_index(p, c, sg, i, &idx)) {
         const ulonglong2 acc = *reinterpret_cast<const ulonglong2*>(st + (r0 + 4 * i) * 36 + 4 * g);
-        const uint64_t r01 = f2_pack(rs[i].x, rs[i].y), r23 = f2_pack(rs[i].z, rs[i].w);
+        uint64_t r01, r23;
+        if (p.raw16 && p.resid) {
+          const float2 lo = Op16<BF16>::unpack(__float_as_uint(rs[i].x)), hi = Op16<BF16>::unpack(__float_as_uint(rs[i].y));
+          r01 = f2_pack(lo.x, lo.y);
+          r23 = f2_pack(hi.x, hi.y);
+        } else {
+          r01 = f2_pack(rs[i].x, rs[i].y);
+          r23 = f2_pack(rs[i].z, rs[i].w);
+        }
         uint64_t v01 = f2_add(acc.x, f2_add(b2.x, r01));
         uint64_t v23 = f2_add(acc.y, f2_add(b2.y, r23));
         if (p.raw_out) {

@@ -37,7 +37,10 @@ def generate_diffusion_cond(model, steps: int = 250, cfg_scale: float = 6,
                             seed: int = -1, device: str = "cuda",
                             init_audio: tp.Optional[tp.Tuple[int, torch.Tensor]] = None, init_noise_level: float = 1.0,
                             mask_args: dict = None, return_latents: bool = False, disable_tqdm: bool = False,
-                            **sampler_kwargs) -> torch.Tensor:
+                            noise: tp.Optional[torch.Tensor] = None, **sampler_kwargs) -> torch.Tensor:
+    """`noise` is the one argument the reference does not have: explicit unit-variance start noise
+    [batch, io_channels, latent length] (inference/distributed.py seeds it per prompt so that a prompt's result does
+    not depend on which rank / batch it lands in); None = the reference's seeded torch.randn draw."""
     if model.conditioner is not None:
         model.conditioner.set_device(device)
     audio_sample_size = sample_size
@@ -59,7 +62,12 @@ def generate_diffusion_cond(model, steps: int = 250, cfg_scale: float = 6,
 
     seed = seed if seed != -1 else np.random.randint(0, 2**32 - 1, dtype=np.uint32)
     torch.manual_seed(int(seed))
-    noise = torch.randn([num_sample, model.io_channels, sample_size], device=device)
+    if noise is None:
+        noise = torch.randn([num_sample, model.io_channels, sample_size], device=device)
+    elif tuple(noise.shape) != (num_sample, model.io_channels, sample_size):
+        raise ValueError(f"noise must have shape {(num_sample, model.io_channels, sample_size)}, got {tuple(noise.shape)}")
+    else:
+        noise = noise.to(device)
 
     mask = None
     if init_audio is not None:

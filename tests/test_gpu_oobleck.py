@@ -3,8 +3,8 @@ reference modules and against the CPU oracle, through the drop-in modules (ctype
 
 Tolerance: the native convolutions use fp16 operands with fp32 accumulation and an fp32
 residual stream; the reference (TF32 disabled, inference/generation.py:165-166) is fp32.
-Gate: rel-L2 <= 3e-3 on the decoded audio (~50 dB SNR) for the 3-stage golden model with fp16
-operands (2.5e-2 for bf16).  Through the full 5-stage / 37-convolution SA-Open stack with synthetic
+Gate: rel-L2 <= 4e-3 on the decoded audio (~48 dB SNR) for the 3-stage golden model with fp16
+operands and an fp16 skip stream (2.5e-2 for bf16 operands, fp32 skip stream).  Through the full 5-stage / 37-convolution SA-Open stack with synthetic
 weights the operand rounding itself is amplified to ~1e-2 (every Snake has slope up to 1 + e^alpha/e^beta),
 so those tests measure that floor with the oracle (same fp32 arithmetic, conv operands rounded to fp16:
 oobleck_oracle.operand_rounding) and require the GPU result to be within 2x of it."""
@@ -16,7 +16,7 @@ import torch
 from helpers import load_golden, rel_l2
 
 pytestmark = pytest.mark.gpu
-TOL = {"fp16": 3e-3, "bf16": 2.5e-2}
+TOL = {"fp16": 4e-3, "bf16": 2.5e-2}     # fp16: operands AND the skip stream are fp16 since round 2 (3.3e-3 measured)
 
 
 def _build(dtype="fp16"):
