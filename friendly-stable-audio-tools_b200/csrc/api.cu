@@ -62,6 +62,8 @@ int satb_attention(const void* q16, const void* k16, const void* v16, void* o16,
                              static_cast<cudaStream_t>(stream));
 }
 
+int satb_debug_attention_occupancy(int dyn_smem, int carveout_pct) { return debug_attention_occupancy(dyn_smem, carveout_pct); }
+
 // Debug: same as satb_attention, plus a clock64 trace of one CTA into dbg[tiles * 12] (device memory).
 int satb_attention_trace(const void* q16, const void* k16, const void* v16, void* o16, int B, int H, int Hkv, int Nq,
                          int Nk, int bf16, unsigned long long* dbg, void* stream) {

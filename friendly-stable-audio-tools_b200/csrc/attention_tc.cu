@@ -294,6 +294,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     *sm_slot = p.sm_slots ? static_cast<uint32_t>(atomicAdd(p.sm_slots + smid, 1)) & 1u : 0u;
+    if (p.dbg) {   // per-CTA residency record: SM id, slot, start time (ns)
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.dbg[192 + blockIdx.x * 4 + 0] = smid;
+      p.dbg[192 + blockIdx.x * 4 + 1] = *sm_slot;
+      p.dbg[192 + blockIdx.x * 4 + 2] = t;
+    }
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, kTmemColsAttn);
@@ -351,7 +358,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int j = 0; j < n_tiles; ++j, ++g) {
           const int st = g % kStagesKV;
           mbar_wait(&k_full[st], (g / kStagesKV) & 1);
-          if (g >= 1) mbar_wait(s_free, (g - 1) & 1);   // S of the previous tile is in the softmax registers
+          // latency-critical: polled, not a suspending try_wait (the wake-up of a suspended issuer thread was measured
+          // at ~1000 cycles between the softmax's arrive and S being full again)
+          if (g >= 1) mbar_spin(s_free, (g - 1) & 1);   // S of the previous tile is in the softmax registers
           tc_fence_after();
           const int nk = min(kK, p.Nk - j * kK);
           const int n_mma = (nk + 15) & ~15;
@@ -375,8 +384,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
         for (int j = 0; j < n_tiles; ++j, ++g) {
           const int st = g % kStagesKV;
-          mbar_wait(p_ready, g & 1);
           mbar_wait(&v_full[st], (g / kStagesKV) & 1);
+          mbar_spin(p_ready, g & 1);                    // polled: see the Q K^T issuer
           if (j == 0 && i >= 1) mbar_wait(o_free, (i - 1) & 1);   // the previous unit's O has been read out
           tc_fence_after();
           const int nk = min(kK, p.Nk - j * kK);
@@ -416,12 +425,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t s_addr = t_lane + kColS, p_addr = t_lane + kColP, o_addr = t_lane + kColO;
     const float sc = p.scale_log2;
     const bool trace = p.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
-    // The two resident CTAs of an SM start together and, being identical, would stay in lockstep: both exponentiate
-    // (sharing the SFU) and then both sit in their per-tile bookkeeping with the SFU idle.  The odd one therefore
-    // starts its softmax half a tile period late; the offset persists (neither CTA waits for the other).
-    if (odd_cta)
-      while (clock64() - t_start < p.stagger) {
-      }
     int g = 0, i = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
       int b, h, q0;
@@ -433,10 +436,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int j = 0; j < n_tiles; ++j, ++g) {
         const int nk = min(kK, p.Nk - j * kK);
         const int nch = (nk + 31) >> 5;   // 32-column chunks holding real keys
-        if (trace && g < 16) p.dbg[g * 4 + 0] = clock64();
-        mbar_wait(s_full, g & 1);
+        if (trace && g < 16) p.dbg[g * 12 + 0] = clock64();
+        mbar_spin(s_full, g & 1);
         tc_fence_after();
-        if (trace && g < 16) p.dbg[g * 4 + 1] = clock64();
+        if (g == 0 && odd_cta) {
+          // The two resident CTAs of an SM start together and, being identical, would stay in lockstep: both
+          // exponentiate (sharing the SFU) and then both sit in their per-tile bookkeeping with the SFU idle.  The odd
+          // one therefore starts its first tile half a period late; the offset persists (neither waits for the other).
+          const long long t0 = clock64();
+          while (clock64() - t0 < p.stagger) {
+          }
+        }
+        if (trace && g < 16) p.dbg[g * 12 + 1] = clock64();
         if (!warp_active) {
           tc_fence_before();
           mbar_arrive(s_free);
@@ -445,18 +456,26 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           continue;
         }
         uint32_t ra[32], rb[32];
-        // raw max of the valid columns of a chunk
         auto cmax = [&](int c, const uint32_t (&r)[32]) -> float {
-          float mx = -INFINITY;
           const int lim = nk - c * 32;
           if (lim >= 32) {
+            // four independent chains of 3-input maxima (a single chain is 16 dependent instructions)
+            float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[e]), __uint_as_float(r[e + 1])));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (e < lim) mx = fmaxf(mx, __uint_as_float(r[e]));
+            for (int e = 4; e < 28; e += 8) {
+              m0 = fmaxf(m0, fmaxf(__uint_as_float(r[e]), __uint_as_float(r[e + 1])));
+              m1 = fmaxf(m1, fmaxf(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])));
+              m2 = fmaxf(m2, fmaxf(__uint_as_float(r[e + 4]), __uint_as_float(r[e + 5])));
+              m3 = fmaxf(m3, fmaxf(__uint_as_float(r[e + 6]), __uint_as_float(r[e + 7])));
+            }
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(r[28]), __uint_as_float(r[29])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(r[30]), __uint_as_float(r[31])));
+            return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
           }
+          float mx = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (e < lim) mx = fmaxf(mx, __uint_as_float(r[e]));
           return mx;
         };
         // P chunk = exp2(S c - m_ref) as packed 16-bit pairs in w[]; returns the fp32 row sum of the chunk
@@ -503,6 +522,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tmem_ld_32x32(s_addr, ra);
         if (nch > 1) tmem_ld_32x32(s_addr + 32, rb);
         tmem_ld_wait();
+        if (trace && g < 16) p.dbg[g * 12 + 2] = clock64();
         float mx_raw = cmax(0, ra);
         if (nch > 1) mx_raw = fmaxf(mx_raw, cmax(1, rb));
         // the first tile of a unit fixes the reference max from its first (up to) 64 keys; should a later key of the
@@ -510,18 +530,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (j == 0) m_ref = mx_raw * sc;
         uint32_t w0[16], w1[16];
         float sum = cexp(0, ra, w0);
+        if (trace && g < 16) p.dbg[g * 12 + 3] = clock64();
         if (nch > 2) tmem_ld_32x32(s_addr + 64, ra);
         if (nch > 1) sum += cexp(1, rb, w1);
+        if (trace && g < 16) p.dbg[g * 12 + 4] = clock64();
         if (nch > 3) tmem_ld_32x32(s_addr + 96, rb);
         if (g >= 1) {
-          mbar_wait(p_free, (g - 1) & 1);   // P V of the previous tile retired: P may be overwritten, O is quiescent
+          mbar_spin(p_free, (g - 1) & 1);   // P V of the previous tile retired: P may be overwritten, O is quiescent
           tc_fence_after();
         }
-        if (trace && g < 16) p.dbg[g * 4 + 2] = clock64();
+        if (trace && g < 16) p.dbg[g * 12 + 5] = clock64();
         tmem_st_32x16(p_addr, w0);
         if (nch > 1) tmem_st_32x16(p_addr + 16, w1);
+        if (trace && g < 16) p.dbg[g * 12 + 6] = clock64();
         if (nch > 2) {
           tmem_ld_wait();
+          if (trace && g < 16) p.dbg[g * 12 + 7] = clock64();
           mx_raw = fmaxf(mx_raw, cmax(2, ra));
           if (nch > 3) mx_raw = fmaxf(mx_raw, cmax(3, rb));
         }
@@ -530,14 +554,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (!__any_sync(0xffffffffu, need)) {
           tc_fence_before();
           mbar_arrive(s_free);              // every column of S is in registers: Q K_{j+1}^T may overwrite it
+          if (trace && g < 16) p.dbg[g * 12 + 8] = clock64();
           if (nch > 2) {
             sum += cexp(2, ra, w0);
             tmem_st_32x16(p_addr + 32, w0);
           }
+          if (trace && g < 16) p.dbg[g * 12 + 9] = clock64();
           if (nch > 3) {
             sum += cexp(3, rb, w1);
             tmem_st_32x16(p_addr + 48, w1);
           }
+          if (trace && g < 16) p.dbg[g * 12 + 10] = clock64();
         } else {
           const float m_new = need ? mx_raw * sc : m_ref;
           const float f = ex2_approx(m_ref - m_new);   // 1 for rows that keep their reference
@@ -572,10 +599,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(p_ready);
-        if (trace && g < 16) p.dbg[g * 4 + 3] = clock64();
+        if (trace && g < 16) p.dbg[g * 12 + 11] = clock64();
       }
       // epilogue of the unit: O / l -> global (128 B per row)
-      mbar_wait(o_done, i & 1);
+      mbar_spin(o_done, i & 1);
       tc_fence_after();
       uint32_t r0[32], r1[32];
       tmem_ld_32x32(o_addr, r0);
@@ -605,6 +632,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (p.dbg && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.dbg[192 + blockIdx.x * 4 + 3] = t;
+  }
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemColsAttn);
@@ -671,7 +703,12 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
   }
   const int row_tasks = batch * H * a.n_rows;
   int grid = a.n_units > row_tasks ? a.n_units : row_tasks;
-  const int slots = 2 * device_sm_count();
+  static int ctas_per_sm = -1;
+  if (ctas_per_sm < 0) {
+    const char* e = getenv("SATB_ATTN_CTAS_PER_SM");   // 1: one CTA per SM (A/B measurement of the SFU sharing)
+    ctas_per_sm = (e && atoi(e) == 1) ? 1 : 2;
+  }
+  const int slots = ctas_per_sm * device_sm_count();
   if (grid > slots) grid = slots;
   if (grid <= 0) return 0;
   static PerDeviceOnce attr16, attrbf;
@@ -703,6 +740,17 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
   count_launch();
   SATB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+// Debug: resident CTAs per SM the runtime reports for the attention kernel with `dyn_smem` bytes of dynamic shared
+// memory and the given carveout preference (percent, -1 = leave unchanged); tests / profiling only.
+int debug_attention_occupancy(int dyn_smem, int carveout_pct) {
+  auto kern = attn_tc_kernel<false>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem) != cudaSuccess) return -1;
+  if (carveout_pct >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct);
+  int nb = -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, dyn_smem) != cudaSuccess) return -2;
+  return nb;
 }
 
 }  // namespace satb

@@ -10,6 +10,7 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
                         int64_t ldo, int64_t q_bs, int64_t k_bs, int64_t v_bs, int64_t o_bs, int q_cols, int k_cols,
                         int v_cols, int q_col, int k_col, int v_col, int batch, int H, int H_kv, int Nq, int Nk,
                         bool bf16, cudaStream_t stream, unsigned long long* dbg = nullptr);
+int debug_attention_occupancy(int dyn_smem, int carveout_pct);
 // debugging switches (environment variables; the defaults are the production path)
 bool conv_halo_enabled();     // SATB_CONV_HALO=off: generic 7-tap loads for the final conv (A/B debugging)
 bool resunit_use_fused();      // SATB_RESUNIT=unfused runs the 128-channel ResidualUnits as two GEMM launches (A/B debugging)

@@ -117,7 +117,11 @@ int satb_sampler_update(const float* x, const float* v, const float* den_1, cons
 int satb_attention(const void* q16, const void* k16, const void* v16, void* o16, int B, int H, int Hkv, int Nq, int Nk,
                    int bf16, void* stream);
 
-/* satb_attention plus a clock64 trace (per 64-key tile: 12 slots) of one CTA, for profiles/. */
+/* Debug / profiling: resident CTAs per SM reported by the runtime for the attention kernel with the given dynamic
+ * shared-memory size and carveout preference (percent, -1 = unchanged). */
+int satb_debug_attention_occupancy(int dyn_smem, int carveout_pct);
+/* satb_attention plus a clock64 trace (16 key tiles x 12 slots) of CTA 0's first softmax warp followed by one
+ * (SM id, slot, start ns, end ns) record per CTA: dbg must hold 16 * 12 + 4 * gridDim entries (<= 1376). */
 int satb_attention_trace(const void* q16, const void* k16, const void* v16, void* o16, int B, int H, int Hkv, int Nq,
                          int Nk, int bf16, unsigned long long* dbg, void* stream);
 

@@ -134,3 +134,32 @@ def import_reference():
     ns.generation = ref_modules["stable_audio_tools.inference.generation"]
     ns.sampling = ref_modules["stable_audio_tools.inference.sampling"]
     return ns
+
+
+class reference_modules:
+    """with reference_modules(ref): ... -> the reference package is what `import stable_audio_tools...` resolves to
+    (its factories import their siblings lazily, e.g. models/factory.py:7-9); the drop-in package's modules are
+    restored on exit."""
+
+    def __init__(self, ref):
+        self.ref = ref
+
+    @staticmethod
+    def _ours():
+        return {k: v for k, v in sys.modules.items() if k == "stable_audio_tools" or k.startswith("stable_audio_tools.")}
+
+    def __enter__(self):
+        self.saved = self._ours()
+        for k in self.saved:
+            del sys.modules[k]
+        sys.modules.update(self.ref.modules)
+        sys.path.insert(0, REFERENCE_ROOT)
+        return self
+
+    def __exit__(self, *exc):
+        sys.path.remove(REFERENCE_ROOT)
+        self.ref.modules.update(self._ours())      # keep lazily imported reference modules for the next use
+        for k in list(sys.modules):
+            if k == "stable_audio_tools" or k.startswith("stable_audio_tools."):
+                del sys.modules[k]
+        sys.modules.update(self.saved)

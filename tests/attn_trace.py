@@ -4,16 +4,29 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "friendly-stable-audio-tools_b200"))
 import torch
 from stable_audio_tools import _native as nat
-B, H, N = 8, 24, 1025
+B, H, N = 8, 24, int(sys.argv[1]) if len(sys.argv) > 1 else 1025
 q = torch.randn(B, N, H * 64, device="cuda").half(); k = torch.randn(B, N, H * 64, device="cuda").half()
 v = torch.randn(B, N, H * 64, device="cuda").half(); o = torch.empty_like(q)
-dbg = torch.zeros(16 * 4, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(16 * 12 + 4 * 296, dtype=torch.int64, device="cuda")
 for _ in range(3):
     nat.check(nat.lib().satb_attention_trace(nat.ptr(q), nat.ptr(k), nat.ptr(v), nat.ptr(o), B, H, H, N, N, 0, nat.ptr(dbg), nat.stream_ptr()))
 torch.cuda.synchronize()
-d = dbg.cpu().view(16, 4)
+allv = dbg.cpu()
+d = allv[:192].view(16, 12)
 t0 = int(d[0, 0])
-names = ["tile_begin", "s_full", "p_free", "p_ready"]
-print("tile " + " ".join(f"{n:>12s}" for n in names))
+names = ["begin", "s_full", "ld01", "exp0", "exp1", "p_free", "st01", "ld23", "s_free", "exp2", "exp3", "p_ready"]
+print("tile " + " ".join(f"{n:>8s}" for n in names))
 for j in range(16):
-    print(f"{j:4d} " + " ".join(f"{int(d[j, i]) - t0:12d}" for i in range(4)))
+    print(f"{j:4d} " + " ".join(f"{int(d[j, i]) - t0:8d}" for i in range(12)))
+
+res = allv[192:].view(296, 4)
+t_min = int(res[:, 2][res[:, 2] > 0].min())
+by_sm = {}
+for c in range(296):
+    sm, slot, a, b = (int(v) for v in res[c])
+    if a:
+        by_sm.setdefault(sm, []).append((c, slot, (a - t_min) / 1e3, (b - t_min) / 1e3))
+overl = sum(1 for v in by_sm.values() if len(v) == 2 and max(v[0][2], v[1][2]) < min(v[0][3], v[1][3]))
+print(f"{len(by_sm)} SMs used; SMs whose two CTAs overlap in time: {overl}")
+for sm in sorted(by_sm)[:6]:
+    print("  SM", sm, [(c, slot, round(a, 1), round(b, 1)) for c, slot, a, b in by_sm[sm]])

@@ -149,3 +149,27 @@ def test_stream_decode_int16_matches_the_per_sample_path():
             ref = float_to_int16_audio(decode_fn(lat[i:i + 1])[0], maximize=maximize)
             assert g.dtype == torch.int16 and g.shape == ref.shape
             assert int((g.int() - ref.int()).abs().max()) <= 1, (i, maximize)   # at most one LSB
+
+
+def test_generate_sharded_per_prompt_results_do_not_depend_on_the_world_size():
+    """inference/distributed.generate_sharded with the native model: the clips of 5 prompts generated as one rank
+    (batches of 2) equal, prompt by prompt and bit for bit, the clips generated as ranks 0 and 1 of a world of 2
+    (shards 0,2,4 / 1,3; here run one after the other on the same GPU: per-prompt seeding makes every clip
+    independent of its batch mates; the 2-process gloo version of this test runs on CPU in test_host_logic.py)."""
+    from stable_audio_tools.inference.distributed import generate_sharded
+    model, cfg, dit_sd, dec_cfg, dsd = _build()
+    n, L = 5, 40
+    g = torch.Generator().manual_seed(9)
+    cond_all = {"prompt": (torch.randn(n, 10, 128, generator=g).cuda(), torch.ones(n, 10).cuda()),
+                "seconds_start": (torch.randn(n, 1, 128, generator=g).cuda(), torch.ones(n, 1).cuda()),
+                "seconds_total": (torch.randn(n, 1, 128, generator=g).cuda(), torch.ones(n, 1).cuda())}
+    kw = dict(conditioning_tensors=cond_all, steps=4, cfg_scale=4.0, sample_size=L * 64, batch_size=2, seed=5,
+              sigma_min=0.3, sigma_max=50.0, device="cuda")
+    one = dict(generate_sharded(model, rank=0, world_size=1, **kw))
+    assert sorted(one) == list(range(n)) and one[0].shape == (2, L * 64)
+    for r in (0, 1):
+        part = generate_sharded(model, rank=r, world_size=2, **kw)
+        assert [i for i, _ in part] == list(range(n))[r::2]
+        for i, y in part:
+            assert torch.equal(y, one[i]), (r, i)
+    assert not torch.equal(one[0], one[1])
