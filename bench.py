@@ -303,6 +303,10 @@ def run_native(args):
             td.barrier()
         torch.cuda.synchronize()
 
+    # one denoiser call = one CUDA-graph launch (DiffusionTransformer.cuda_graph; MultistepSdeStepper.run() switches it
+    # on by itself, bench.py drives step() directly); --no-graph measures the plain enqueue path
+    dit = wrapper.model
+    dit.cuda_graph = not args.no_graph
     loop = Loop()
     for _ in range(max(args.warmup, 3)):
         loop.step()
@@ -373,6 +377,7 @@ def run_native(args):
     # ---------------- same K steps again with per-kernel-class CUDA events (roofline) ---------
     # (a second pass: event records between kernels would defeat the programmatic dependent
     # launches the timed region above benefits from)
+    dit.cuda_graph = False                                        # events between kernels: eager enqueue
     _native.check(lib.satb_dit_profile(h_dit, 1))
     _native.check(lib.satb_dit_profile_read(h_dit, ms8, cnt8))   # clear
     barrier()
@@ -385,6 +390,7 @@ def run_native(args):
     profiled_ms_per_step = p0.elapsed_time(p1) / args.steps
     _native.check(lib.satb_dit_profile_read(h_dit, ms8, cnt8))
     _native.check(lib.satb_dit_profile(h_dit, 0))
+    dit.cuda_graph = not args.no_graph
 
     # ---------------- Oobleck decode of the batch (audio-seconds/s of a full generation) ------
     lat = loop.x / max(float(loop.x.abs().max()), 1.0)
@@ -476,6 +482,7 @@ def run_native(args):
                      # algorithmic A + W + out = 163.7 MB, part of the 16-bit output stays in the 126 MB L2)
                      "traffic": 125806592, "traffic_unit": "bytes per launch (ncu)", "peak_source": peak_src,
                      "avg_launch_ms": ff_in_ms},
+        "cuda_graph": not args.no_graph,
         "step_tflops": step_tflops, "step_frac_of_peak": step_tflops / peak_tf,
         "step_frac_of_burst_peak": (step_tflops / peak_burst) if peak_burst else None,
         "profiled_pass_ms_per_step": profiled_ms_per_step, "host_enqueue_ms_per_step": host_enqueue_ms,
@@ -531,6 +538,8 @@ def main():
                          "the metric is quoted on), 4 = batch 8 per GPU (64 prompts on 8 GPUs), 5 = SA-2.0 length")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="enqueue every kernel of a step instead of "
+                    "replaying the captured CUDA graph of the denoiser call")
     args = ap.parse_args()
     set_config(args.config)
     if args.impl == "reference":

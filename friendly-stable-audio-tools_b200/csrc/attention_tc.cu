@@ -1,30 +1,33 @@
 // tcgen05 attention forward, head dim 64, no mask, non-causal, optional GQA:
 //   O = softmax(Q K^T / sqrt(64)) V      (reference models/transformer.py:496-536)
 //
-// Persistent kernel, two CTAs per SM (2 x 256 TMEM columns, 2 x 85 KB shared memory).  A work unit is 128 query
-// rows of one (batch item, head); CTA c processes units c, c + grid, ... without re-initialising anything.  Keys
-// are processed in tiles of 128:
+// Persistent kernel, two CTAs of 384 threads per SM (2 x 256 TMEM columns, 2 x 86 KB shared memory).  A work unit is
+// 128 query rows of one (batch item, head); CTA c processes units c, c + grid, ... without re-initialising anything.
+// Keys are processed in tiles of 128:
 //   warp 0 (one thread)  TMA producer: Q of the unit, K / V tiles (2-stage rings)
 //   warp 1 (one thread)  S = Q K_j^T -> TMEM (tcgen05.mma, smem operands) as soon as S has been read out
 //   warp 3 (one thread)  O += P V_j (A = P from TMEM, B = V tile addressed MN-major)
-//   warps 4-7            one query row per thread: P = exp2(S c - m_ref) -> TMEM as packed 16-bit pairs, row sum
-//                        (fp32) and raw row max in registers; chunks of 32 columns are software-pipelined
-//                        (tcgen05.ld of chunk c+2 in flight while chunk c is exponentiated).  S is handed back to the
-//                        MMA thread right after its LAST chunk has been loaded into registers, so Q K_{j+1}^T runs
-//                        under the exponentials of that chunk.
+//   warps 4-11           softmax: warps w and w + 4 own the same 32 query rows (TMEM lane quadrant w % 4) and split the
+//                        128 key columns of a tile; per 32-column chunk: tcgen05.ld -> row max -> P = exp2(S c - m_ref)
+//                        -> packed 16-bit pairs back to TMEM; row sums in fp32 registers.
 //   warp 2               TMEM allocator; afterwards the CUDA-core path for ragged query rows (below)
-// TMEM columns: S [0,128)  P [128,192)  O [192,256).  The softmax is SFU-bound (16 ex2 / clk / SM, 202 M exponentials
-// per SA-Open layer): what matters is that the two resident CTAs keep the SFU busy, i.e. that each warp's fixed
-// per-tile cost (barrier waits, TMEM load / store latency) stays below the exponentiation time of a tile - hence
-// 128-key tiles (1024 SFU cycles per warp and tile).
+// TMEM columns: S [0,128)  P [128,192)  O [192,256).
+// Why eight softmax warps: the softmax is bound by the SFU (16 ex2 / clk / SM = one MUFU.EX2 warp instruction per
+// 8 cycles and scheduler; 202 M exponentials per SA-Open layer) only if every scheduler always has a warp with
+// exponentials to issue.  A lone warp per scheduler reaches 12.8 cycles per MUFU (in-order issue behind the FFMA2 /
+// F2FP / FADD2 of its own stream) and spends as long again in tcgen05.ld / st / mbarrier latencies per tile; with
+// two such warps (two CTAs of four softmax warps) the CTAs fall into lockstep - both exponentiate, then both wait -
+// (measured, profiles/r02_attention_*.txt).  Four warps per scheduler cover those latencies.
 // O stays in TMEM for the whole unit: the reference max m_ref only moves when a tile's row max exceeds it by more
 // than 2^8 (lazy rescale: exponentials stay <= 256, sums in fp32), so the O rescale (TMEM load-scale-store) and the
 // recomputation of that tile's P are rare.
 //
-// Ragged query rows: with Nq = 1025 = 8 * 128 + 1 (the prepended conditioning token) a ninth tensor-core tile per
-// (item, head) would hold ONE row and cost as much time as a full one.  When Nq % 128 <= kRowPathMax those rows are
-// computed by warp 2 on CUDA cores instead (one warp per row: lane-per-key dot products, online softmax over
-// blocks of 1024 keys, lane-per-two-dims P V), concurrently with the tensor-core pipeline of the same CTA.
+// Ragged shapes (1025 = 8 * 128 + 1 tokens: the prepended conditioning token):
+//   * leftover KEYS (Nk % 128 <= kExtraMax) do not get a tile of their own - a whole pipeline step for one column -:
+//     every softmax thread computes its row's score against them on CUDA cores (q from the Q tile in shared memory)
+//     and adds exp2(.) v to its O row in the epilogue, in fp32;
+//   * leftover QUERY rows (Nq % 128 <= kRowPathMax) are computed by warp 2 on CUDA cores (one warp per row:
+//     eight lanes per key, online softmax over blocks of 1024 keys), concurrently with the tensor-core pipeline.
 #include "common.cuh"
 #include "gemm.cuh"
 #include "kernels.h"
@@ -42,9 +45,14 @@ constexpr int kStagesKV = 2;
 constexpr int kQBytes = kQ * kD * 2;                         // 16 KB
 constexpr int kKVBytes = kK * kD * 2;                        // 16 KB
 constexpr int kRowChunk = 1024;                              // keys per block of the CUDA-core row path
-constexpr int kRowBatch = 16;                                // independent 16-byte loads in flight per lane (row path)
+constexpr int kRowBatch = 8;                                 // independent 16-byte loads in flight per lane (row path)
 constexpr int kRowPathMax = 2;                               // Nq % 128 <= this: those rows take the row path
-constexpr int kAttnSmem = kQBytes + 2 * kStagesKV * kKVBytes + kRowChunk * 4 + 256 + 1024;   // 85.25 KB: two CTAs per SM
+constexpr int kAttnThreads = 384;                            // 4 control warps + 8 softmax warps
+constexpr int kSoftmaxThreads = 256;
+constexpr int kExtraMax = 2;                                 // Nk % 128 <= this: those keys are added in the epilogue
+constexpr int kXRows = 16;                                   // rows of the leftover-key K / V tiles (TMA box)
+constexpr int kXBytes = kXRows * kD * 2;                     // 2 KB
+constexpr int kAttnSmem = kQBytes + 2 * kStagesKV * kKVBytes + 4 * kXBytes + kRowChunk * 4 + 4 * 2 * kQ * 4 + 256 + 1024;   // 97.25 KB
 constexpr int kTmemColsAttn = 256;
 constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;
 constexpr float kRescaleThreshold = 8.0f;                    // log2 units
@@ -54,14 +62,13 @@ struct AttnTcArgs {
   int64_t ldo, o_bs;
   int Nq, Nk, group, H, batch;
   int q_col, k_col, v_col;   // column offsets (elements) of head 0 inside the q / k / v tensors
+  int n_tiles, n_extra;      // key tiles on the tensor cores; leftover keys (Nk - 128 n_tiles <= kExtraMax) added in the epilogue
   int n_qt;                  // tensor-core query tiles per (item, head)
   int n_units;               // batch * H * n_qt
   int row0, n_rows;          // rows [row0, row0 + n_rows) of every (item, head) take the CUDA-core path
   const uint16_t *q, *k, *v; // raw pointers for the row path
   int64_t ldq, ldk, ldv, q_bs, k_bs, v_bs;
   float scale_log2;
-  int* sm_slots;             // [>= number of SMs] running counters: the two CTAs of an SM draw consecutive values
-  int stagger;               // cycles by which the odd CTA of an SM delays its softmax (see the kernel)
   unsigned long long* dbg;   // optional clock64 trace of CTA 0's first softmax warp (tests / profiles only)
 };
 
@@ -241,42 +248,50 @@ __device__ void attn_row_path(const AttnTcArgs& p, int b, int h, int row, float*
 }
 
 template <bool BF16>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-               const __grid_constant__ CUtensorMap tmV, const AttnTcArgs p) {
+               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKx,
+               const __grid_constant__ CUtensorMap tmVx, const AttnTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // [16 KB] (single: the last Q K^T of a unit is issued a whole
                                                         // tile before the unit ends, which is the time the next Q has to arrive)
   uint8_t* sK = smem + kQBytes;                         // [kStagesKV][16 KB]
   uint8_t* sV = sK + kStagesKV * kKVBytes;
-  float* prow = reinterpret_cast<float*>(sV + kStagesKV * kKVBytes);   // [kRowChunk] row-path scratch
-  uint64_t* bars = reinterpret_cast<uint64_t*>(prow + kRowChunk);
-  uint64_t* q_full = bars;                 // [1] (+1 unused)
-  uint64_t* q_empty = bars + 2;            // [1] (+1 unused)
-  uint64_t* k_full = bars + 4;             // [kStagesKV]
+  uint8_t* sX = sV + kStagesKV * kKVBytes;              // [2 units][K | V][2 KB] leftover-key rows (16-row TMA boxes)
+  float* prow = reinterpret_cast<float*>(sX + 4 * kXBytes);            // [kRowChunk] row-path scratch
+  float* xch = prow + kRowChunk;                        // [4][2][128] exchange between the two column halves of a row:
+                                                        // slots 0 / 1 = tile parity, 2 = first-tile max, 3 = row sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 4 * 2 * kQ);
+  uint64_t* q_full = bars;                 // TMA -> MMA / softmax: Q of the unit has landed
+  uint64_t* q_empty = bars + 1;            // MMA (+ softmax, when it reads Q for leftover keys) -> TMA
+  uint64_t* k_full = bars + 2;             // [kStagesKV]
   uint64_t* k_empty = k_full + kStagesKV;
   uint64_t* v_full = k_empty + kStagesKV;
   uint64_t* v_empty = v_full + kStagesKV;
   uint64_t* s_full = v_empty + kStagesKV;  // MMA -> softmax: S holds Q K_j^T
-  uint64_t* s_free = s_full + 1;           // softmax -> MMA: S has been read into registers (128 arrivals)
-  uint64_t* p_ready = s_free + 1;          // softmax -> MMA: P written (128 arrivals)
+  uint64_t* s_free = s_full + 1;           // softmax -> MMA: S has been read (256 arrivals)
+  uint64_t* p_ready = s_free + 1;          // softmax -> MMA: P written (256 arrivals)
   uint64_t* p_free = p_ready + 1;          // MMA -> softmax: P V_j retired (P reusable, O up to date)
   uint64_t* o_done = p_free + 1;           // MMA -> softmax: last P V of the unit retired
-  uint64_t* o_free = o_done + 1;           // softmax -> MMA: O of the previous unit has been read (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
-  uint32_t* sm_slot = tmem_slot + 1;       // 0 / 1: which of the SM's two resident CTAs this is
+  uint64_t* o_free = o_done + 1;           // softmax -> MMA: O of the previous unit has been read (256 arrivals)
+  uint64_t* x_full = o_free + 1;           // [2] TMA -> softmax: leftover-key K / V rows of the unit have landed
+  uint64_t* x_empty = x_full + 2;          // [2] softmax -> TMA: they have been used (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = (p.Nk + kK - 1) / kK;
+  const int n_tiles = p.n_tiles;           // tensor-core key tiles; the n_extra leftover keys are added in the epilogue
+  const int n_extra = p.n_extra;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, n_extra > 0 ? 1 + kSoftmaxThreads : 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_empty[i], kSoftmaxThreads);
     }
     for (int i = 0; i < kStagesKV; ++i) {
       mbar_init(&k_full[i], 1);
@@ -285,20 +300,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(p_ready, 128);
+    mbar_init(s_free, kSoftmaxThreads);
+    mbar_init(p_ready, kSoftmaxThreads);
     mbar_init(p_free, 1);
     mbar_init(o_done, 1);
-    mbar_init(o_free, 128);
+    mbar_init(o_free, kSoftmaxThreads);
     fence_mbar_init();
-    uint32_t smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    *sm_slot = p.sm_slots ? static_cast<uint32_t>(atomicAdd(p.sm_slots + smid, 1)) & 1u : 0u;
-    if (p.dbg) {   // per-CTA residency record: SM id, slot, start time (ns)
+    if (p.dbg) {   // per-CTA residency record: SM id, start time (ns)
+      uint32_t smid;
       unsigned long long t;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       p.dbg[192 + blockIdx.x * 4 + 0] = smid;
-      p.dbg[192 + blockIdx.x * 4 + 1] = *sm_slot;
       p.dbg[192 + blockIdx.x * 4 + 2] = t;
     }
   }
@@ -310,8 +323,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const bool odd_cta = *sm_slot != 0;
-  const long long t_start = clock64();
   pdl_launch_dependents();
   pdl_wait();
 
@@ -332,9 +343,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         int b, h, q0;
         unit_coords(u, b, h, q0);
         const int hk = h / p.group;
-        mbar_wait(&q_empty[0], (i & 1) ^ 1);
-        mbar_expect_tx(&q_full[0], kQBytes);
-        tma_load_4d(sQ, &tmQ, &q_full[0], p.q_col + h * kD, 0, q0, b);
+        mbar_wait(q_empty, (i & 1) ^ 1);
+        mbar_expect_tx(q_full, kQBytes);
+        tma_load_4d(sQ, &tmQ, q_full, p.q_col + h * kD, 0, q0, b);
+        if (n_extra > 0) {               // the unit's leftover keys: 16-row boxes (rows past Nk are zero-filled)
+          const int xb = i & 1;
+          mbar_wait(&x_empty[xb], ((i >> 1) & 1) ^ 1);
+          mbar_expect_tx(&x_full[xb], 2 * kXBytes);
+          tma_load_4d(sX + xb * 2 * kXBytes, &tmKx, &x_full[xb], p.k_col + hk * kD, 0, n_tiles * kK, b);
+          tma_load_4d(sX + xb * 2 * kXBytes + kXBytes, &tmVx, &x_full[xb], p.v_col + hk * kD, 0, n_tiles * kK, b);
+        }
         for (int j = 0; j < n_tiles; ++j, ++g) {
           const int st = g % kStagesKV;
           const uint32_t ph = ((g / kStagesKV) & 1) ^ 1;
@@ -353,14 +371,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       int g = 0, i = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
         const uint32_t q_addr = smem_u32(sQ);
-        mbar_wait(&q_full[0], i & 1);
+        mbar_wait(q_full, i & 1);
         tc_fence_after();
         for (int j = 0; j < n_tiles; ++j, ++g) {
           const int st = g % kStagesKV;
           mbar_wait(&k_full[st], (g / kStagesKV) & 1);
-          // latency-critical: polled, not a suspending try_wait (the wake-up of a suspended issuer thread was measured
-          // at ~1000 cycles between the softmax's arrive and S being full again)
-          if (g >= 1) mbar_spin(s_free, (g - 1) & 1);   // S of the previous tile is in the softmax registers
+          if (g >= 1) mbar_spin(s_free, (g - 1) & 1);   // S of the previous tile has been read by every softmax thread
           tc_fence_after();
           const int nk = min(kK, p.Nk - j * kK);
           const int n_mma = (nk + 15) & ~15;
@@ -373,7 +389,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           umma_commit(&k_empty[st]);   // the K tile is free as soon as these MMAs retire
           umma_commit(s_full);
         }
-        umma_commit(&q_empty[0]);      // every Q K^T of this unit has retired: the Q buffer may be refilled
+        umma_commit(q_empty);          // every Q K^T of this unit has retired (immediately, if there was none)
       }
     }
   } else if (warp == 3) {
@@ -385,7 +401,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int j = 0; j < n_tiles; ++j, ++g) {
           const int st = g % kStagesKV;
           mbar_wait(&v_full[st], (g / kStagesKV) & 1);
-          mbar_spin(p_ready, g & 1);                    // polled: see the Q K^T issuer
+          mbar_spin(p_ready, g & 1);
           if (j == 0 && i >= 1) mbar_wait(o_free, (i - 1) & 1);   // the previous unit's O has been read out
           tc_fence_after();
           const int nk = min(kK, p.Nk - j * kK);
@@ -417,49 +433,69 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         attn_row_path<BF16>(p, b, h, p.row0 + r, prow, lane);
       }
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------- softmax + epilogue (1 row / thread)
-    const int q = warp - 4;
+  } else {
+    // ------------------------------------------------------- softmax + epilogue
+    // Eight warps: warp w may touch TMEM lanes 32 (w % 4) .. +31, so warps w and w + 4 share the 32 query rows of a
+    // quadrant and split the key columns of every tile (half 0: keys 0-63, half 1: keys 64-127).  Four warps per
+    // scheduler (two CTAs per SM) keep the SFU fed while others sit in TMEM / barrier latencies.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t s_addr = t_lane + kColS, p_addr = t_lane + kColP, o_addr = t_lane + kColO;
     const float sc = p.scale_log2;
     const bool trace = p.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
+    // exchange slot s: this thread writes xch[s][half][row] and reads xch[s][1 - half][row] after the pair barrier
+    auto xput = [&](int slot, float v) { xch[(slot * 2 + half) * kQ + row] = v; };
+    auto xget = [&](int slot) -> float { return xch[(slot * 2 + (half ^ 1)) * kQ + row]; };
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };   // the two warps of a quadrant
     int g = 0, i = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
       int b, h, q0;
       unit_coords(u, b, h, q0);
-      // a warp whose 32 rows are all beyond Nq (partial last query tile) only keeps the barrier protocol going;
-      // its P rows are never read back through O
-      const bool warp_active = (q0 + q * 32) < p.Nq;
+      const int hk = h / p.group;
       float m_ref = -INFINITY, l = 0.f;
+      // ---- leftover keys (Nk % 128 <= kExtraMax): their scores on CUDA cores, from the Q tile in shared memory
+      float s_x[kExtraMax];
+#pragma unroll
+      for (int e = 0; e < kExtraMax; ++e) s_x[e] = -INFINITY;
+      const uint8_t* xk = sX + (i & 1) * 2 * kXBytes;   // K rows of the leftover keys; V rows follow at + kXBytes
+      if (n_extra > 0) {
+        mbar_spin(q_full, i & 1);
+        mbar_spin(&x_full[i & 1], (i >> 1) & 1);
+#pragma unroll
+        for (int e = 0; e < kExtraMax; ++e) {
+          if (e < n_extra) {
+            float acc = 0.f;
+#pragma unroll 2
+            for (int c = 0; c < kD / 8; ++c) {
+              // 128B-swizzled K-major tiles: 16-byte chunk c of row r sits at chunk position c ^ (r % 8)
+              const uint4 qv = *reinterpret_cast<const uint4*>(sQ + row * 128 + ((c ^ (row & 7)) << 4));
+              const uint4 kv = *reinterpret_cast<const uint4*>(xk + e * 128 + ((c ^ e) << 4));   // same address in every lane
+              const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w}, kw[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+              for (int d = 0; d < 4; ++d) {
+                const float2 a = Op16<BF16>::unpack(qw[d]), bb = Op16<BF16>::unpack(kw[d]);
+                acc = fmaf(a.x, bb.x, fmaf(a.y, bb.y, acc));
+              }
+            }
+            s_x[e] = acc;
+          }
+        }
+        mbar_arrive(q_empty);            // this thread is done with Q
+      }
+      if (trace && g < 16) p.dbg[g * 12 + 2] = clock64();
       for (int j = 0; j < n_tiles; ++j, ++g) {
         const int nk = min(kK, p.Nk - j * kK);
-        const int nch = (nk + 31) >> 5;   // 32-column chunks holding real keys
+        const int c0 = 2 * half;                 // this thread's chunks of 32 keys: c0, c0 + 1
+        const int lim0 = nk - c0 * 32, lim1 = lim0 - 32;   // valid keys in them (may be <= 0)
         if (trace && g < 16) p.dbg[g * 12 + 0] = clock64();
         mbar_spin(s_full, g & 1);
         tc_fence_after();
-        if (g == 0 && odd_cta) {
-          // The two resident CTAs of an SM start together and, being identical, would stay in lockstep: both
-          // exponentiate (sharing the SFU) and then both sit in their per-tile bookkeeping with the SFU idle.  The odd
-          // one therefore starts its first tile half a period late; the offset persists (neither waits for the other).
-          const long long t0 = clock64();
-          while (clock64() - t0 < p.stagger) {
-          }
-        }
         if (trace && g < 16) p.dbg[g * 12 + 1] = clock64();
-        if (!warp_active) {
-          tc_fence_before();
-          mbar_arrive(s_free);
-          if (g >= 1) mbar_wait(p_free, (g - 1) & 1);
-          mbar_arrive(p_ready);
-          continue;
-        }
-        uint32_t ra[32], rb[32];
-        auto cmax = [&](int c, const uint32_t (&r)[32]) -> float {
-          const int lim = nk - c * 32;
+        uint32_t r[32];
+        auto cmax = [&](int lim) -> float {      // raw max of the valid columns of the chunk in r[]
           if (lim >= 32) {
-            // four independent chains of 3-input maxima (a single chain is 16 dependent instructions)
             float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
 #pragma unroll
             for (int e = 4; e < 28; e += 8) {
@@ -478,30 +514,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             if (e < lim) mx = fmaxf(mx, __uint_as_float(r[e]));
           return mx;
         };
-        // P chunk = exp2(S c - m_ref) as packed 16-bit pairs in w[]; returns the fp32 row sum of the chunk
-        auto cexp = [&](int c, const uint32_t (&r)[32], uint32_t (&w)[16]) -> float {
+        // P chunk = exp2(S c - m_ref) of r[] -> TMEM columns [pcol, pcol + 16); returns the fp32 row sum
+        auto cexp_store = [&](int lim, uint32_t pcol) -> float {
+          uint32_t w[16];
           float sum;
-          const int lim = nk - c * 32;
           if (lim >= 32) {
-            // three phases, so that the 32 MUFU.EX2 are issued back to back and none of their consumers waits on a
-            // result that is still in the SFU pipeline (a lone warp per scheduler cannot hide that latency)
             const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_ref, -m_ref);
-            float t[32];
+            uint64_t sum2 = pack2(0.f, 0.f);
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              unpack2(ffma2(pack2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), sc2, nm2), t[2 * e], t[2 * e + 1]);
-#pragma unroll
-            for (int e = 0; e < 32; ++e) t[e] = ex2_ordered(t[e]);
-            uint64_t sum2a = pack2(0.f, 0.f), sum2b = pack2(0.f, 0.f);
-#pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-              sum2a = fadd2(sum2a, pack2(t[2 * e], t[2 * e + 1]));
-              sum2b = fadd2(sum2b, pack2(t[2 * e + 2], t[2 * e + 3]));
-              w[e] = Op16<BF16>::pack(t[2 * e], t[2 * e + 1]);
-              w[e + 1] = Op16<BF16>::pack(t[2 * e + 2], t[2 * e + 3]);
+            for (int e = 0; e < 16; ++e) {
+              float t0, t1;
+              unpack2(ffma2(pack2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), sc2, nm2), t0, t1);
+              const float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+              sum2 = fadd2(sum2, pack2(p0, p1));
+              w[e] = Op16<BF16>::pack(p0, p1);
             }
             float a0, a1;
-            unpack2(fadd2(sum2a, sum2b), a0, a1);
+            unpack2(sum2, a0, a1);
             sum = a0 + a1;
           } else {
             sum = 0.f;
@@ -515,119 +544,173 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               w[e] = Op16<BF16>::pack(p0, p1);
             }
           }
+          tmem_st_32x16(pcol, w);
           return sum;
         };
-        // ---- pipelined pass: exponentials of chunks 0,1 (kept in registers) while 2,3 load and while P V of the
-        // previous tile retires -> store them -> release S -> exponentials of chunks 2,3
-        tmem_ld_32x32(s_addr, ra);
-        if (nch > 1) tmem_ld_32x32(s_addr + 32, rb);
-        tmem_ld_wait();
-        if (trace && g < 16) p.dbg[g * 12 + 2] = clock64();
-        float mx_raw = cmax(0, ra);
-        if (nch > 1) mx_raw = fmaxf(mx_raw, cmax(1, rb));
-        // the first tile of a unit fixes the reference max from its first (up to) 64 keys; should a later key of the
-        // tile exceed it by more than 2^8 the lazy-rescale path below recomputes the tile
-        if (j == 0) m_ref = mx_raw * sc;
-        uint32_t w0[16], w1[16];
-        float sum = cexp(0, ra, w0);
-        if (trace && g < 16) p.dbg[g * 12 + 3] = clock64();
-        if (nch > 2) tmem_ld_32x32(s_addr + 64, ra);
-        if (nch > 1) sum += cexp(1, rb, w1);
-        if (trace && g < 16) p.dbg[g * 12 + 4] = clock64();
-        if (nch > 3) tmem_ld_32x32(s_addr + 96, rb);
-        if (g >= 1) {
-          mbar_spin(p_free, (g - 1) & 1);   // P V of the previous tile retired: P may be overwritten, O is quiescent
-          tc_fence_after();
+        const uint32_t sa0 = s_addr + c0 * 32, sa1 = sa0 + 32, pa0 = p_addr + c0 * 16, pa1 = pa0 + 16;
+        if (j == 0) {
+          // first tile of the unit: the reference max = max over the whole first tile (both halves) and the leftover keys
+          float mx = -INFINITY;
+          if (lim0 > 0) {
+            tmem_ld_32x32(sa0, r);
+            tmem_ld_wait();
+            mx = cmax(lim0);
+          }
+          if (lim1 > 0) {
+            tmem_ld_32x32(sa1, r);
+            tmem_ld_wait();
+            mx = fmaxf(mx, cmax(lim1));
+          }
+#pragma unroll
+          for (int e = 0; e < kExtraMax; ++e) mx = fmaxf(mx, s_x[e]);
+          xput(2, mx);
+          pair_sync();
+          m_ref = fmaxf(mx, xget(2)) * sc;
         }
-        if (trace && g < 16) p.dbg[g * 12 + 5] = clock64();
-        tmem_st_32x16(p_addr, w0);
-        if (nch > 1) tmem_st_32x16(p_addr + 16, w1);
-        if (trace && g < 16) p.dbg[g * 12 + 6] = clock64();
-        if (nch > 2) {
+        // ---- hot path: chunk 0: load -> max -> exp2 -> P store; chunk 1: load -> max; exchange of the tile max between
+        // the halves; S is released (Q K_{j+1}^T runs under the exponentials of chunk 1); chunk 1: exp2 -> P store
+        float mx_raw = -INFINITY, sum = 0.f;
+        bool waited = false;
+        auto wait_p_free = [&]() {
+          if (!waited && g >= 1) {
+            mbar_spin(p_free, (g - 1) & 1);      // P V of the previous tile retired: P may be overwritten, O is quiescent
+            tc_fence_after();
+          }
+          waited = true;
+        };
+        if (lim0 > 0) {
+          tmem_ld_32x32(sa0, r);
           tmem_ld_wait();
-          if (trace && g < 16) p.dbg[g * 12 + 7] = clock64();
-          mx_raw = fmaxf(mx_raw, cmax(2, ra));
-          if (nch > 3) mx_raw = fmaxf(mx_raw, cmax(3, rb));
+          mx_raw = cmax(lim0);
+          wait_p_free();
+          sum = cexp_store(lim0, pa0);
         }
-        // lazy rescale: only when this tile's max exceeds the reference max by more than 2^8
-        const bool need = mx_raw * sc > m_ref + kRescaleThreshold;
-        if (!__any_sync(0xffffffffu, need)) {
+        if (trace && g < 16) p.dbg[g * 12 + 3] = clock64();
+        if (lim1 > 0) {
+          tmem_ld_32x32(sa1, r);
+          tmem_ld_wait();
+          mx_raw = fmaxf(mx_raw, cmax(lim1));
+        }
+        // lazy rescale: only when the tile's row max (over BOTH halves) exceeds the reference max by more than 2^8
+        xput(g & 1, mx_raw);
+        pair_sync();
+        const float mx_tile = fmaxf(mx_raw, xget(g & 1));
+        const bool need = mx_tile * sc > m_ref + kRescaleThreshold;
+        if (!__any_sync(0xffffffffu, need)) {    // both warps of the quadrant see the same rows, i.e. decide alike
           tc_fence_before();
-          mbar_arrive(s_free);              // every column of S is in registers: Q K_{j+1}^T may overwrite it
-          if (trace && g < 16) p.dbg[g * 12 + 8] = clock64();
-          if (nch > 2) {
-            sum += cexp(2, ra, w0);
-            tmem_st_32x16(p_addr + 32, w0);
+          mbar_arrive(s_free);                   // this thread holds its last chunk in registers
+          if (lim1 > 0) {
+            wait_p_free();
+            sum += cexp_store(lim1, pa1);
           }
-          if (trace && g < 16) p.dbg[g * 12 + 9] = clock64();
-          if (nch > 3) {
-            sum += cexp(3, rb, w1);
-            tmem_st_32x16(p_addr + 48, w1);
-          }
-          if (trace && g < 16) p.dbg[g * 12 + 10] = clock64();
         } else {
-          const float m_new = need ? mx_raw * sc : m_ref;
+          wait_p_free();
+          const float m_new = need ? mx_tile * sc : m_ref;
           const float f = ex2_approx(m_ref - m_new);   // 1 for rows that keep their reference
           m_ref = m_new;
           l *= f;
-          if (j > 0) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t r[32];
-              tmem_ld_32x32(o_addr + c * 32, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                uint32_t w[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) w[e] = __float_as_uint(__uint_as_float(r[half * 16 + e]) * f);
-                tmem_st_32x16(o_addr + c * 32 + half * 16, w);
-              }
-            }
-          }
-          sum = 0.f;                        // P again, all chunks, with the new reference max
-          for (int c = 0; c < nch; ++c) {
-            tmem_ld_32x32(s_addr + c * 32, ra);
+          sum = 0.f;                             // P again with the new reference max: chunk 1 from registers ...
+          if (lim1 > 0) sum = cexp_store(lim1, pa1);
+          if (lim0 > 0) {                        // ... chunk 0 from S, which has not been released yet
+            tmem_ld_32x32(sa0, r);
             tmem_ld_wait();
-            sum += cexp(c, ra, w0);
-            tmem_st_32x16(p_addr + c * 16, w0);
+            sum += cexp_store(lim0, pa0);
           }
           tc_fence_before();
           mbar_arrive(s_free);
+          if (j > 0) {                           // each half rescales its 32 columns of O
+            tmem_ld_32x32(o_addr + half * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t w[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) w[e] = __float_as_uint(__uint_as_float(r[hh * 16 + e]) * f);
+              tmem_st_32x16(o_addr + half * 32 + hh * 16, w);
+            }
+          }
         }
+        if (trace && g < 16) p.dbg[g * 12 + 4] = clock64();
         l += sum;
+        wait_p_free();                           // (threads without valid keys in this tile have not waited yet)
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(p_ready);
         if (trace && g < 16) p.dbg[g * 12 + 11] = clock64();
       }
-      // epilogue of the unit: O / l -> global (128 B per row)
-      mbar_spin(o_done, i & 1);
-      tc_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32(o_addr, r0);
-      tmem_ld_32x32(o_addr + 32, r1);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(o_free);                  // O is in registers: the next unit's first P V may overwrite it
-      const float inv = 1.0f / l;
-      const bool valid = (q0 + row) < p.row0;   // row0 = Nq, or the first row of the CUDA-core path
-      if (valid) {
-        uint16_t* og = p.o + b * p.o_bs + static_cast<int64_t>(q0 + row) * p.ldo + static_cast<int64_t>(h) * kD;
-        uint4* dst = reinterpret_cast<uint4*>(og);
+      // ---- epilogue of the unit: (O + leftover keys) / l -> global; each half stores 32 of the 64 columns, in two
+      // passes of 16 (the 80-register budget of a 384-thread CTA does not hold a 32-column row plus the extras)
+      const int gt = g - 1;                      // trace row of the unit's last tile
+      if (trace && gt >= 0 && gt < 16) p.dbg[gt * 12 + 5] = clock64();
+      if (n_tiles == 0) {
+        // no tensor-core tile at all (Nk <= kExtraMax): the reference max comes from the leftover keys alone
+        float mx = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          dst[e] = make_uint4(Op16<BF16>::pack(__uint_as_float(r0[8 * e]) * inv, __uint_as_float(r0[8 * e + 1]) * inv),
-                              Op16<BF16>::pack(__uint_as_float(r0[8 * e + 2]) * inv, __uint_as_float(r0[8 * e + 3]) * inv),
-                              Op16<BF16>::pack(__uint_as_float(r0[8 * e + 4]) * inv, __uint_as_float(r0[8 * e + 5]) * inv),
-                              Op16<BF16>::pack(__uint_as_float(r0[8 * e + 6]) * inv, __uint_as_float(r0[8 * e + 7]) * inv));
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          dst[4 + e] = make_uint4(Op16<BF16>::pack(__uint_as_float(r1[8 * e]) * inv, __uint_as_float(r1[8 * e + 1]) * inv),
-                                  Op16<BF16>::pack(__uint_as_float(r1[8 * e + 2]) * inv, __uint_as_float(r1[8 * e + 3]) * inv),
-                                  Op16<BF16>::pack(__uint_as_float(r1[8 * e + 4]) * inv, __uint_as_float(r1[8 * e + 5]) * inv),
-                                  Op16<BF16>::pack(__uint_as_float(r1[8 * e + 6]) * inv, __uint_as_float(r1[8 * e + 7]) * inv));
+        for (int e = 0; e < kExtraMax; ++e) mx = fmaxf(mx, s_x[e]);
+        m_ref = mx * sc;
       }
+      float p_x[kExtraMax];
+#pragma unroll
+      for (int e = 0; e < kExtraMax; ++e) {
+        p_x[e] = e < n_extra ? ex2_approx(fmaf(s_x[e], sc, -m_ref)) : 0.f;   // fp32: no range issue whatever the score
+        if (half == 0) l += p_x[e];
+      }
+      xput(3, l);
+      pair_sync();
+      const float inv = 1.0f / (l + xget(3));
+      if (n_tiles > 0) {
+        mbar_spin(o_done, i & 1);
+        tc_fence_after();
+      }
+      if (trace && gt >= 0 && gt < 16) p.dbg[gt * 12 + 6] = clock64();
+      const bool valid = (q0 + row) < p.row0;    // row0 = Nq, or the first row of the CUDA-core path
+      uint16_t* og = p.o + b * p.o_bs + static_cast<int64_t>(q0 + row) * p.ldo + static_cast<int64_t>(h) * kD + half * 32;
+      const uint8_t* xv = xk + kXBytes;
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        uint32_t ro[16];
+        if (n_tiles > 0) {
+          tmem_ld_32x16(o_addr + half * 32 + sub * 16, ro);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) ro[e] = 0u;
+        }
+        float ov[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) ov[e] = __uint_as_float(ro[e]);
+        if (n_extra > 0) {
+#pragma unroll
+          for (int e = 0; e < kExtraMax; ++e) {
+            if (e < n_extra) {
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                const uint4 vv = *reinterpret_cast<const uint4*>(xv + e * 128 + (((half * 4 + sub * 2 + c) ^ e) << 4));
+                const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                  const float2 f2 = Op16<BF16>::unpack(vw[d]);
+                  ov[c * 8 + 2 * d] = fmaf(p_x[e], f2.x, ov[c * 8 + 2 * d]);
+                  ov[c * 8 + 2 * d + 1] = fmaf(p_x[e], f2.y, ov[c * 8 + 2 * d + 1]);
+                }
+              }
+            }
+          }
+        }
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(og + sub * 16);
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            dst[e] = make_uint4(Op16<BF16>::pack(ov[8 * e] * inv, ov[8 * e + 1] * inv), Op16<BF16>::pack(ov[8 * e + 2] * inv, ov[8 * e + 3] * inv),
+                                Op16<BF16>::pack(ov[8 * e + 4] * inv, ov[8 * e + 5] * inv), Op16<BF16>::pack(ov[8 * e + 6] * inv, ov[8 * e + 7] * inv));
+        }
+      }
+      if (n_tiles > 0) {
+        tc_fence_before();
+        mbar_arrive(o_free);                     // O has been read: the next unit's first P V may overwrite it
+      }
+      if (n_extra > 0) mbar_arrive(&x_empty[i & 1]);   // this thread is done with the unit's leftover-key rows
+      if (trace && gt >= 0 && gt < 16) p.dbg[gt * 12 + 10] = clock64();
     }
   }
   tc_fence_before();
@@ -667,6 +750,9 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
   SATB_PROPAGATE(make_tmap_rows(&tq, q, q_cols, Nq, batch, ldq, q_bs, kQ));
   SATB_PROPAGATE(make_tmap_rows(&tk, k, k_cols, Nk, batch, ldk, k_bs, kK));
   SATB_PROPAGATE(make_tmap_rows(&tv, v, v_cols, Nk, batch, ldv, v_bs, kK));
+  CUtensorMap tkx, tvx;   // the leftover keys (rows 128 n_tiles ...) as 16-row boxes
+  SATB_PROPAGATE(make_tmap_rows(&tkx, k, k_cols, Nk, batch, ldk, k_bs, kXRows));
+  SATB_PROPAGATE(make_tmap_rows(&tvx, v, v_cols, Nk, batch, ldv, v_bs, kXRows));
   AttnTcArgs a;
   a.o = static_cast<uint16_t*>(o);
   a.ldo = ldo; a.o_bs = o_bs;
@@ -678,29 +764,18 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
   const bool row_path = rem != 0 && rem <= kRowPathMax;
   a.n_qt = Nq / kQ + ((rem != 0 && !row_path) ? 1 : 0);
   a.n_units = batch * H * a.n_qt;
+  // keys: full 128-key tiles on the tensor cores; a remainder of <= kExtraMax keys in the epilogue, a larger one as one
+  // more (partial) tile
+  const int krem = Nk % kK;
+  const bool extra = krem != 0 && krem <= kExtraMax;
+  a.n_tiles = Nk / kK + ((krem != 0 && !extra) ? 1 : 0);
+  a.n_extra = extra ? krem : 0;
   a.row0 = row_path ? Nq - rem : Nq;
   a.n_rows = row_path ? rem : 0;
   a.q = static_cast<const uint16_t*>(q); a.k = static_cast<const uint16_t*>(k); a.v = static_cast<const uint16_t*>(v);
   a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.q_bs = q_bs; a.k_bs = k_bs; a.v_bs = v_bs;
   a.scale_log2 = (1.0f / sqrtf(64.0f)) * 1.4426950408889634f;
   a.dbg = dbg;
-  {
-    static int* slots[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) dev = 0;
-    if (!slots[dev]) {   // once per device (first call = warm-up, never inside a graph capture)
-      SATB_CHECK_CUDA(cudaMalloc(&slots[dev], 1024 * sizeof(int)));
-      SATB_CHECK_CUDA(cudaMemset(slots[dev], 0, 1024 * sizeof(int)));
-    }
-    a.sm_slots = slots[dev];
-    static int stagger = -1;
-    if (stagger < 0) {
-      const char* e = getenv("SATB_ATTN_STAGGER");   // cycles; tuning / A-B only
-      stagger = e ? atoi(e) : 1100;
-    }
-    a.stagger = stagger;
-  }
   const int row_tasks = batch * H * a.n_rows;
   int grid = a.n_units > row_tasks ? a.n_units : row_tasks;
   static int ctas_per_sm = -1;
@@ -719,7 +794,7 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
     if (getenv("SATB_ATTN_DEBUG")) {
       int nb = -1, dev = 0, sm_smem = 0, rsv = 0, regs = 0;
       cudaGetDevice(&dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, kAttnSmem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kAttnThreads, kAttnSmem);
       cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
       cudaDeviceGetAttribute(&rsv, cudaDevAttrReservedSharedMemoryPerBlock, dev);
       cudaDeviceGetAttribute(&regs, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
@@ -732,10 +807,10 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
   };
   if (bf16) {
     if (attrbf.first()) SATB_PROPAGATE(prepare(attn_tc_kernel<true>));
-    SATB_CHECK_CUDA(launch_pdl(attn_tc_kernel<true>, dim3(grid), dim3(256), kAttnSmem, stream, tq, tk, tv, a));
+    SATB_CHECK_CUDA(launch_pdl(attn_tc_kernel<true>, dim3(grid), dim3(kAttnThreads), kAttnSmem, stream, tq, tk, tv, tkx, tvx, a));
   } else {
     if (attr16.first()) SATB_PROPAGATE(prepare(attn_tc_kernel<false>));
-    SATB_CHECK_CUDA(launch_pdl(attn_tc_kernel<false>, dim3(grid), dim3(256), kAttnSmem, stream, tq, tk, tv, a));
+    SATB_CHECK_CUDA(launch_pdl(attn_tc_kernel<false>, dim3(grid), dim3(kAttnThreads), kAttnSmem, stream, tq, tk, tv, tkx, tvx, a));
   }
   count_launch();
   SATB_CHECK_CUDA(cudaGetLastError());
@@ -749,7 +824,7 @@ int debug_attention_occupancy(int dyn_smem, int carveout_pct) {
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem) != cudaSuccess) return -1;
   if (carveout_pct >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct);
   int nb = -1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, dyn_smem) != cudaSuccess) return -2;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kAttnThreads, dyn_smem) != cudaSuccess) return -2;
   return nb;
 }
 

@@ -178,6 +178,7 @@ extern "C" {
 const char* satb_last_error(void) { return get_last_error(); }
 unsigned long long satb_launch_count(void) { return g_launch_count; }
 void satb_reset_launch_count(void) { g_launch_count = 0; }
+void satb_add_launch_count(unsigned long long n) { g_launch_count += n; }
 int satb_abi_version(void) { return SATB_ABI_VERSION; }
 
 int satb_dit_create(const SatbDitConfig* cfg, SatbDit** out) {

@@ -43,6 +43,7 @@ SIGNATURES = {
     "satb_abi_version": (_I, []),
     "satb_launch_count": (ctypes.c_ulonglong, []),
     "satb_reset_launch_count": (None, []),
+    "satb_add_launch_count": (None, [ctypes.c_ulonglong]),
     "satb_dit_create": (_I, [ctypes.POINTER(SatbDitConfig), ctypes.POINTER(_VP)]),
     "satb_dit_destroy": (None, [_VP]),
     "satb_dit_load_weight": (_I, [_VP, ctypes.c_char_p, _VP, _LL, _VP]),

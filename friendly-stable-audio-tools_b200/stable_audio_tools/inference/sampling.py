@@ -87,6 +87,14 @@ class MultistepSdeStepper:
         self.h_1 = self.h_2 = None
         self.fused = (isinstance(model, VDenoiser) and callback is None and x.is_cuda and x.dtype == torch.float32
                       and x.numel() % 4 == 0)
+        # the native DiT (directly, or as DiTWrapper.model) can run a call as one CUDA-graph launch; its output is then a
+        # static buffer, which is safe here because the fused update consumes v before the next model call
+        self.graph_dit = None
+        if self.fused:
+            inner = getattr(model, "inner_model", None)
+            for cand in (inner, getattr(inner, "model", None)):
+                if cand is not None and hasattr(cand, "cuda_graph") and hasattr(cand, "_graph_forward"):
+                    self.graph_dit = cand
         self.x_in = None                               # x * c_in(sigma_i), produced by the previous fused update
 
     def coeffs(self, i):
@@ -164,8 +172,15 @@ class MultistepSdeStepper:
         return x_next
 
     def run(self):
-        for _ in range(len(self.sig) - 1):
-            self.step()
+        prev = None
+        if self.graph_dit is not None:
+            prev, self.graph_dit.cuda_graph = self.graph_dit.cuda_graph, True
+        try:
+            for _ in range(len(self.sig) - 1):
+                self.step()
+        finally:
+            if self.graph_dit is not None:
+                self.graph_dit.cuda_graph = prev
         return self.x
 
 

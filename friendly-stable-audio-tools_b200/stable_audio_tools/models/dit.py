@@ -95,6 +95,11 @@ class DiffusionTransformer(nn.Module):
         self.__dict__["_cond_key"] = None
         self.__dict__["_keepalive"] = None
         self.__dict__["_neg_masked"] = None
+        self.__dict__["_graph"] = None
+        # cuda_graph = True: one denoiser call = ONE CUDA-graph launch (the ~280 kernel launches of a forward are
+        # captured once per (shape, guidance, conditioning) and replayed).  The returned tensor is then a static
+        # buffer that the NEXT call overwrites - fine for the samplers, which consume it at once; off by default.
+        self.cuda_graph = False
         # nn.Module.load_state_dict on a PARENT (ConditionedDiffusionModelWrapper, DiTWrapper, copy_state_dict(model, sd))
         # recurses through _load_from_state_dict and never calls a child's load_state_dict override; the post hook
         # below is run for every module of the recursion, so the native copy is refreshed whichever way the
@@ -153,6 +158,7 @@ class DiffusionTransformer(nn.Module):
                 _native.check(lib.satb_dit_finalize(self.__dict__["_h"], st))
             self.__dict__["_weights_dirty"] = False
             self.__dict__["_cond_key"] = None
+            self.__dict__["_graph"] = None
         return self.__dict__["_h"]
 
     @staticmethod
@@ -245,9 +251,47 @@ class DiffusionTransformer(nn.Module):
                                                                    float(scale_phi), st))
                 info = {"hidden_states": [hidden.view(-1, L + P, self.embed_dim)]}
                 return self._unpatch(out).to(x.dtype), info
+            if self.cuda_graph and not torch.cuda.is_current_stream_capturing():
+                out = self._graph_forward(h, xin, tin, B, L, float(cfg_scale), float(scale_phi), x.device)
+                return self._unpatch(out).to(x.dtype)
+            self.__dict__["_graph"] = None       # an eager call may regrow workspaces the captured graph points into
             _native.check(_native.lib().satb_dit_forward(h, _native.ptr(xin), _native.ptr(tin), _native.ptr(out), B, L,
                                                          float(cfg_scale), float(scale_phi), st))
             return self._unpatch(out).to(x.dtype)
+
+    def _graph_forward(self, h, xin, tin, B, L, cfg_scale, scale_phi, device):
+        """satb_dit_forward through a captured CUDA graph: the C entry point enqueues on the stream it
+        is given and neither allocates nor synchronises once the workspace exists, so the whole forward - ~280
+        launches with their programmatic-dependent-launch edges - is captured once and replayed with two small
+        device copies (x, t) in front."""
+        lib = _native.lib()
+        key = (B, L, cfg_scale, scale_phi, self.__dict__["_cond_key"], device.index)
+        g = self.__dict__["_graph"]
+        if g is None or g["key"] != key:
+            sx, st_, so = torch.empty_like(xin), torch.empty_like(tin), torch.empty_like(xin)
+            sx.copy_(xin)
+            st_.copy_(tin)
+
+            def run():
+                _native.check(lib.satb_dit_forward(h, _native.ptr(sx), _native.ptr(st_), _native.ptr(so), B, L, cfg_scale,
+                                                   scale_phi, _native.stream_ptr(device)))
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):        # warm-up outside the capture: workspace, tensor maps, attributes
+                run()
+                run()
+            torch.cuda.current_stream(device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            n0 = _native.launch_count()
+            with torch.cuda.graph(graph):
+                run()
+            g = dict(key=key, graph=graph, x=sx, t=st_, out=so, launches=_native.launch_count() - n0)
+            self.__dict__["_graph"] = g
+        g["x"].copy_(xin, non_blocking=True)
+        g["t"].copy_(tin, non_blocking=True)
+        g["graph"].replay()
+        lib.satb_add_launch_count(g["launches"])
+        return g["out"]
 
     def _unpatch(self, out):
         p = self.patch_size

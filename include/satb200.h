@@ -62,6 +62,9 @@ const char* satb_last_error(void);
 int satb_abi_version(void);
 unsigned long long satb_launch_count(void);   /* kernels launched by this library so far */
 void satb_reset_launch_count(void);
+/* Replaying a captured CUDA graph launches kernels this library cannot count: the caller adds the number recorded
+ * while the graph was captured. */
+void satb_add_launch_count(unsigned long long n);
 
 /* ---- DiT: replaces DiffusionTransformer (models/dit.py:14-364) + ContinuousTransformer
  *      (models/transformer.py:705-809) behind DiTWrapper.forward (models/diffusion.py:491-529) */

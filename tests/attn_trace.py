@@ -14,10 +14,10 @@ torch.cuda.synchronize()
 allv = dbg.cpu()
 d = allv[:192].view(16, 12)
 t0 = int(d[0, 0])
-names = ["begin", "s_full", "ld01", "exp0", "exp1", "p_free", "st01", "ld23", "s_free", "exp2", "exp3", "p_ready"]
+names = ["begin", "s_full", "extras", "chunk0", "chunk1", "epi", "o_done", "o_ld", "extraPV", "lsum", "stored", "p_ready"]
 print("tile " + " ".join(f"{n:>8s}" for n in names))
 for j in range(16):
-    print(f"{j:4d} " + " ".join(f"{int(d[j, i]) - t0:8d}" for i in range(12)))
+    print(f"{j:4d} " + " ".join(f"{(int(d[j, i]) - t0) if int(d[j, i]) else 0:8d}" for i in range(12)))
 
 res = allv[192:].view(296, 4)
 t_min = int(res[:, 2][res[:, 2] > 0].min())

@@ -155,3 +155,31 @@ def test_dit_full_size_cfg_is_linear_in_the_scale_and_deterministic():
     d31, d51 = y3 - y1, y5 - y1
     assert rel_l2(d51, 2.0 * d31) < 1e-3
     assert float(d31.norm()) > 1e-3 * float(y1.norm())          # guidance really changes the output
+
+
+def test_dit_cuda_graph_call_equals_the_eager_call():
+    """cuda_graph = True: a denoiser call replayed from a captured CUDA graph gives the bits of the
+    eager call, for new inputs (replay), new conditioning (re-capture) and after an eager call in between."""
+    g, cfg, sd = _golden_case("dit_prepend_small.npz")
+    m = build_native_dit(cfg, sd)
+    T = lambda k: torch.from_numpy(g[k]).cuda()
+    x, t, c, ge = T("x"), T("t"), T("cross"), T("glob")
+    eager = lambda xx, tt, cc: m(xx, tt, cross_attn_cond=cc, global_embed=ge, cfg_scale=7.0).clone()
+    from stable_audio_tools import _native
+    y0 = eager(x, t, c)
+    m.cuda_graph = True
+    n0 = _native.launch_count()
+    y1 = eager(x, t, c)                                   # capture + replay
+    n_capture = _native.launch_count() - n0
+    assert torch.equal(y0, y1)
+    n0 = _native.launch_count()
+    x2, t2 = x * 0.5 + 0.1, (t * 0.7).contiguous()
+    y2 = eager(x2, t2, c)                                 # replay with new inputs
+    assert _native.launch_count() - n0 > 10               # the replayed launches are accounted for
+    c2 = (c * 0.9).contiguous()
+    y3 = eager(x2, t2, c2)                                # new conditioning: prepared again, captured again
+    m.cuda_graph = False
+    assert torch.equal(y2, eager(x2, t2, c)) and torch.equal(y3, eager(x2, t2, c2))
+    m.cuda_graph = True
+    assert torch.equal(y3, eager(x2, t2, c2))             # eager call in between dropped the graph: captured again
+    assert n_capture > 0

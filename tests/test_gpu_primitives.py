@@ -76,7 +76,10 @@ def test_tcgen05_linear_vs_torch(M, N, K, bf16):
 
 
 @pytest.mark.parametrize("B,H,Hkv,Nq,Nk", [(2, 4, 4, 1025, 1025), (1, 24, 12, 1025, 130), (2, 2, 1, 64, 1),
-                                           (1, 3, 3, 65, 191), (1, 24, 24, 300, 300)])
+                                           (1, 3, 3, 65, 191), (1, 24, 24, 300, 300),
+                                           # 2 ragged query rows (CUDA-core row path) x 1 leftover key; only row-path rows;
+                                           # no tensor-core key tile at all (2 keys); many units per CTA
+                                           (1, 2, 2, 130, 257), (1, 2, 1, 2, 130), (2, 4, 2, 128, 2), (3, 24, 24, 1024, 384)])
 def test_attention_vs_oracle(B, H, Hkv, Nq, Nk):
     """softmax(q k^T / 8) v vs the oracle's einsum path (models/transformer.py:510-536), fp16 operands."""
     from oracle.dit_oracle import attention_core
