@@ -32,6 +32,7 @@
 #include "gemm.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
+#include <cmath>
 #include <cstdlib>
 
 namespace satb {
@@ -758,18 +759,28 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
   a.ldo = ldo; a.o_bs = o_bs;
   a.Nq = Nq; a.Nk = Nk; a.group = H / H_kv; a.H = H; a.batch = batch;
   a.q_col = q_col; a.k_col = k_col; a.v_col = v_col;
-  // query rows: full 128-row tiles on the tensor cores; a remainder of <= kRowPathMax rows on CUDA cores, a larger
-  // remainder as one more (partial) tensor-core tile
-  const int rem = Nq % kQ;
-  const bool row_path = rem != 0 && rem <= kRowPathMax;
-  a.n_qt = Nq / kQ + ((rem != 0 && !row_path) ? 1 : 0);
-  a.n_units = batch * H * a.n_qt;
   // keys: full 128-key tiles on the tensor cores; a remainder of <= kExtraMax keys in the epilogue, a larger one as one
   // more (partial) tile
   const int krem = Nk % kK;
   const bool extra = krem != 0 && krem <= kExtraMax;
   a.n_tiles = Nk / kK + ((krem != 0 && !extra) ? 1 : 0);
   a.n_extra = extra ? krem : 0;
+  // query rows: full 128-row tiles on the tensor cores; a remainder of <= kRowPathMax rows either on CUDA cores (warp 2
+  // of the CTAs, concurrently) or as one more, partial, tensor-core tile.  One row task is a serial walk over all keys
+  // by a single warp (~110 cycles per key, measured: 65 us for 1025 keys), so it only pays when every CTA has enough
+  // tensor-core units to hide it behind - large batches; otherwise (B = 1, 2) the partial tile rides in the slack of
+  // the last wave for free.
+  const int rem = Nq % kQ;
+  const int slots_all = 2 * device_sm_count();
+  bool row_path = rem != 0 && rem <= kRowPathMax;
+  if (row_path) {
+    const double unit_cycles = a.n_tiles * 2900.0 + 4500.0, row_cycles = 110.0 * Nk;
+    const double units_per_cta = static_cast<double>(batch) * H * (Nq / kQ) / slots_all;
+    const double rows_per_cta = std::ceil(static_cast<double>(batch) * H * rem / slots_all);
+    if (units_per_cta * unit_cycles < rows_per_cta * row_cycles) row_path = false;
+  }
+  a.n_qt = Nq / kQ + ((rem != 0 && !row_path) ? 1 : 0);
+  a.n_units = batch * H * a.n_qt;
   a.row0 = row_path ? Nq - rem : Nq;
   a.n_rows = row_path ? rem : 0;
   a.q = static_cast<const uint16_t*>(q); a.k = static_cast<const uint16_t*>(k); a.v = static_cast<const uint16_t*>(v);

@@ -17,6 +17,8 @@
 //                               software-pipelined (the load of chunk c+1 overlaps the math of c)
 // The accumulator is double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -66,6 +68,34 @@ struct EpiCtx {
   int L;         // rows per batch item
   int lane;
   float* stage;  // per-warp staging smem (Epi::kStageBytes), or nullptr
+  int n_tile;    // index of the tile along N
+  int half;      // which of the two epilogue warps of the lane quadrant (they take alternate column chunks)
+};
+
+// Epilogues may carry per-thread state across the column chunks of one tile (e.g. the row sums that feed the next
+// LayerNorm): such an epilogue declares `State`, `tile_begin`, `apply(p, c, r, state)` and `tile_end`; all others keep
+// the plain `apply(p, c, r)`.
+template <class E, class = void>
+struct EpiHasState : std::false_type {};
+template <class E>
+struct EpiHasState<E, std::void_t<typename E::State>> : std::true_type {};
+struct EpiNoStateHolder {
+  struct State {};
+};
+template <class Epi>
+struct EpiTile {
+  using State = typename std::conditional<EpiHasState<Epi>::value, Epi, EpiNoStateHolder>::type::State;
+  template <int N>
+  __device__ static __forceinline__ void apply(const typename Epi::Params& p, const EpiCtx& c, const uint32_t (&r)[N], State& st) {
+    if constexpr (EpiHasState<Epi>::value) Epi::apply(p, c, r, st);
+    else Epi::apply(p, c, r);
+  }
+  __device__ static __forceinline__ void begin(const typename Epi::Params& p, const EpiCtx& c, State& st) {
+    if constexpr (EpiHasState<Epi>::value) Epi::tile_begin(p, c, st);
+  }
+  __device__ static __forceinline__ void end(const typename Epi::Params& p, const EpiCtx& c, State& st) {
+    if constexpr (EpiHasState<Epi>::value) Epi::tile_end(p, c, st);
+  }
 };
 
 template <class Epi, int BN, bool BF16>
@@ -225,6 +255,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       c.l0 = m0 + q * 32;
       c.L = s.L;
       c.lane = lane;
+      c.n_tile = nt;
+      c.half = half;
       c.stage = Epi::kStageBytes > 0
                     ? reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStage + 256 + (warp - 4) * Epi::kStageBytes)
                     : nullptr;
@@ -239,6 +271,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_ld_32x32(t_row + ci * Epi::kCols + j * 32, rj);
         }
       };
+      typename EpiTile<Epi>::State est;
+      EpiTile<Epi>::begin(ep, c, est);
       if (half < n_valid) {
         load_chunk(half, r0);
         tmem_ld_wait();
@@ -248,15 +282,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const bool has1 = ci + 2 < n_valid;
         if (has1) load_chunk(ci + 2, r1);
         c.col0 = n0 + ci * Epi::kCols;
-        Epi::apply(ep, c, r0);
+        EpiTile<Epi>::apply(ep, c, r0, est);
         tmem_ld_wait();
         if (has1) {
           if (ci + 4 < n_valid) load_chunk(ci + 4, r0);
           c.col0 = n0 + (ci + 2) * Epi::kCols;
-          Epi::apply(ep, c, r1);
+          EpiTile<Epi>::apply(ep, c, r1, est);
           tmem_ld_wait();
         }
       }
+      EpiTile<Epi>::end(ep, c, est);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -448,6 +483,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       c.l0 = m0 + q * 32;
       c.L = s.L;
       c.lane = lane;
+      c.n_tile = nt;
+      c.half = half;
       c.stage = Epi::kStageBytes > 0
                     ? reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStage + 256 + (warp - 4) * Epi::kStageBytes)
                     : nullptr;
@@ -462,6 +499,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           tmem_ld_32x32(t_row + ci * Epi::kCols + j * 32, rj);
         }
       };
+      typename EpiTile<Epi>::State est;
+      EpiTile<Epi>::begin(ep, c, est);
       if (half < n_valid) {
         load_chunk(half, r0);
         tmem_ld_wait();
@@ -471,15 +510,16 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const bool has1 = ci + 2 < n_valid;
         if (has1) load_chunk(ci + 2, r1);
         c.col0 = n0 + ci * Epi::kCols;
-        Epi::apply(ep, c, r0);
+        EpiTile<Epi>::apply(ep, c, r0, est);
         tmem_ld_wait();
         if (has1) {
           if (ci + 4 < n_valid) load_chunk(ci + 4, r0);
           c.col0 = n0 + (ci + 2) * Epi::kCols;
-          Epi::apply(ep, c, r1);
+          EpiTile<Epi>::apply(ep, c, r1, est);
           tmem_ld_wait();
         }
       }
+      EpiTile<Epi>::end(ep, c, est);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);   // the pair's accumulator lock lives in CTA 0
@@ -501,11 +541,61 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 // Every epilogue receives kCols consecutive fp32 accumulator columns of one row
 // (as raw bits in r[]) and writes them straight to global memory.
 
+// ---- LayerNorm folded into the consumer GEMM (prepend-mode DiT blocks) --------------------------------------------
+// The producer of the residual stream (EpiResidualLN below) stores x16 = 16-bit(h * gamma) next to h and accumulates the
+// row sums s1 = sum h, s2 = sum h^2.  With c[n] = sum_k gamma_k W[n,k] and d[n] = sum_k beta_k W[n,k] (prepared once),
+//   LayerNorm(h) W^T = rstd (h gamma) W^T - rstd mean c + d,   mean = s1 / D, rstd = rsqrt(s2 / D - mean^2 + eps)
+// (models/transformer.py:188-206 followed by the Linear), so the consumer GEMM reads x16 and its epilogue applies one
+// multiply-add per element: no LayerNorm pass over the residual stream, no extra kernel.
+constexpr int kLnSlots = 12;   // partial sums per row: 6 column tiles of 256 x 2 epilogue warps (D = 1536); fixed
+                               // slots summed in a fixed order keep the result bit-reproducible (no atomics)
+struct LnFold {
+  const float2* stats;   // [rows][n_slots] partial (s1, s2) of the residual row, or null: no LayerNorm in front
+  const float* c;        // [N]
+  const float* d;        // [N] or null (beta = 0)
+  float inv_dim;         // 1 / D
+  float eps;
+  int n_slots;
+};
+struct LnRow {
+  float rstd, mr;        // rstd, mean * rstd
+};
+__device__ __forceinline__ LnRow ln_row(const LnFold& f, int row) {
+  const float4* sp = reinterpret_cast<const float4*>(f.stats + static_cast<size_t>(row) * kLnSlots);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnSlots / 2; ++i) {
+    if (2 * i < f.n_slots) {
+      const float4 v = __ldg(sp + i);
+      s1 += v.x + v.z;
+      s2 += v.y + v.w;
+    }
+  }
+  const float mean = s1 * f.inv_dim;
+  const float var = fmaxf(s2 * f.inv_dim - mean * mean, 0.f);
+  LnRow r;
+  r.rstd = rsqrtf(var + f.eps);
+  r.mr = mean * r.rstd;
+  return r;
+}
+// v[0..3] <- rstd * v - (mean rstd) * c[col..col+3] (+ d[col..col+3]); col % 4 == 0 (128-bit loads of c / d)
+__device__ __forceinline__ void ln_apply4(const LnFold& f, const LnRow& r, float& v0, float& v1, float& v2, float& v3, int col) {
+  const float4 cc = __ldg(reinterpret_cast<const float4*>(f.c + col));
+  v0 = fmaf(v0, r.rstd, -r.mr * cc.x);
+  v1 = fmaf(v1, r.rstd, -r.mr * cc.y);
+  v2 = fmaf(v2, r.rstd, -r.mr * cc.z);
+  v3 = fmaf(v3, r.rstd, -r.mr * cc.w);
+  if (f.d) {
+    const float4 dd = __ldg(reinterpret_cast<const float4*>(f.d + col));
+    v0 += dd.x; v1 += dd.y; v2 += dd.z; v3 += dd.w;
+  }
+}
+
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 // out16[row, col] = act(acc + bias)   (act: 0 none, 1 SiLU)
-template <bool BF16>
-struct EpiStore16 {
+template <bool BF16, bool LN = false>   // LN: a LayerNorm is folded into this GEMM (LnFold); separate instantiation so that
+struct EpiStore16 {                      // the plain epilogue carries none of its code or registers
   static constexpr int kCols = 32;
   static constexpr int kStageBytes = 0;
   struct Params {
@@ -513,17 +603,29 @@ struct EpiStore16 {
     int ld;
     const float* bias;  // may be null
     int act;
+    LnFold ln = LnFold{nullptr, nullptr, nullptr, 0.f, 0.f, 0};
   };
   __device__ static __forceinline__ void apply(const Params& p, const EpiCtx& c, const uint32_t (&r)[32]) {
     if (!c.valid) return;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if constexpr (LN) {
+      const LnRow lr = ln_row(p.ln, c.row);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) ln_apply4(p.ln, lr, v[j], v[j + 1], v[j + 2], v[j + 3], c.col0 + j);
+    }
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c.col0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
     uint32_t o[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
-      if (p.bias) {
-        a += __ldg(p.bias + c.col0 + 2 * j);
-        b += __ldg(p.bias + c.col0 + 2 * j + 1);
-      }
+      float a = v[2 * j], b = v[2 * j + 1];
       if (p.act == 1) {
         a = silu_f(a);
         b = silu_f(b);
@@ -601,11 +703,104 @@ struct EpiResidual {
   }
 };
 
+// Residual stream update that also prepares the NEXT LayerNorm (see LnFold): h = h + acc + bias is written back in
+// fp32 (plain load / store: every element belongs to exactly one lane of one tile), x16 = 16-bit(h * gamma) is what
+// the next GEMM reads, and the partial row sums of this tile go to a fixed slot of stats.  Rows below `split` are
+// followed by one LayerNorm (gamma_lo, stats_lo: the cross-attention norm of the conditional rows), the others by
+// another (gamma_hi, stats_hi: the feed-forward norm of rows without cross-attention).
+template <bool BF16>
+struct EpiResidualLN {
+  static constexpr int kCols = 32;
+  static constexpr int kStageBytes = 32 * 36 * 4;   // per-warp [32 rows][32 + 4 pad] fp32 transpose tile
+  struct Params {
+    float* h;
+    int ld;
+    const float* bias;       // may be null
+    void* x16;               // [rows, ld] 16-bit
+    const float* gamma_lo;   // may be null (= 1)
+    const float* gamma_hi;
+    float2* stats_lo;        // may be null (no LayerNorm follows: last block)
+    float2* stats_hi;
+    int split;               // rows < split: *_lo, else *_hi
+  };
+  // Warp-cooperative like EpiConv: the accumulator chunk (thread = row, 32 columns) goes through the per-warp smem
+  // tile so that every global access is a coalesced 128 B row segment (8 lanes x 16 B, 4 rows per instruction); the
+  // old h values are requested BEFORE the transpose so the loads are in flight meanwhile.  Lane = (row offset
+  // lane / 8 within groups of 4 rows, 4-column group lane % 8): it owns rows l0 + lane / 8 + 4 i, i < 8.
+  struct State {
+    float s1[8], s2[8];
+  };
+  __device__ static __forceinline__ void tile_begin(const Params&, const EpiCtx&, State& st) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st.s1[i] = st.s2[i] = 0.f;
+  }
+  __device__ static __forceinline__ void apply(const Params& p, const EpiCtx& c, const uint32_t (&r)[32], State& st) {
+    const int g = c.lane & 7, r0 = c.lane >> 3;
+    const int col = c.col0 + 4 * g;
+    float4 old[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int l = c.l0 + r0 + 4 * i;
+      old[i] = l < c.L ? *reinterpret_cast<const float4*>(p.h + (static_cast<size_t>(c.batch) * c.L + l) * p.ld + col)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float* stg = c.stage;
+    {
+      float4* mine = reinterpret_cast<float4*>(stg + c.lane * 36);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        mine[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                              __uint_as_float(r[4 * j + 3]));
+    }
+    __syncwarp();
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), glo = make_float4(1.f, 1.f, 1.f, 1.f), ghi = glo;
+    if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    if (p.gamma_lo) glo = __ldg(reinterpret_cast<const float4*>(p.gamma_lo + col));
+    if (p.gamma_hi) ghi = __ldg(reinterpret_cast<const float4*>(p.gamma_hi + col));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int l = c.l0 + r0 + 4 * i;
+      if (l < c.L) {
+        const size_t row = static_cast<size_t>(c.batch) * c.L + l;
+        const float4 a = *reinterpret_cast<const float4*>(stg + (r0 + 4 * i) * 36 + 4 * g);
+        float4 v;
+        v.x = a.x + b4.x + old[i].x; v.y = a.y + b4.y + old[i].y; v.z = a.z + b4.z + old[i].z; v.w = a.w + b4.w + old[i].w;
+        *reinterpret_cast<float4*>(p.h + row * p.ld + col) = v;
+        st.s1[i] += (v.x + v.y) + (v.z + v.w);
+        st.s2[i] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, st.s2[i]))));
+        const float4 gg = static_cast<int>(row) < p.split ? glo : ghi;
+        *reinterpret_cast<uint2*>(static_cast<uint16_t*>(p.x16) + row * p.ld + col) =
+            make_uint2(Op16<BF16>::pack(v.x * gg.x, v.y * gg.y), Op16<BF16>::pack(v.z * gg.z, v.w * gg.w));
+      }
+    }
+    __syncwarp();
+  }
+  __device__ static __forceinline__ void tile_end(const Params& p, const EpiCtx& c, State& st) {
+    const int g = c.lane & 7, r0 = c.lane >> 3;
+    const int slot = c.n_tile * 2 + c.half;      // one writer per (row, slot): plain store, summed by ln_row in order
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = st.s1[i], b = st.s2[i];
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {            // the 8 lanes of a row segment (same lane / 8)
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      const int l = c.l0 + r0 + 4 * i;
+      if (g == 0 && l < c.L && slot < kLnSlots) {
+        const size_t row = static_cast<size_t>(c.batch) * c.L + l;
+        float2* sp = static_cast<int>(row) < p.split ? p.stats_lo : p.stats_hi;
+        if (sp) sp[row * kLnSlots + slot] = make_float2(a, b);
+      }
+    }
+  }
+};
+
 // Fused QKV projection epilogue: split is implicit (q | k | v are column ranges of
 // one [M, 3D] buffer); partial rotary on the first 32 dims of every 64-wide q and k
 // head (models/transformer.py:158-183,438-452): pairs (i, i+16), position = token
 // index within the sequence (prepend token = position 0).  fp32 math, then cast.
-template <bool BF16>
+template <bool BF16, bool LN = false>
 struct EpiQkvRope {
   static constexpr int kCols = 32;
   static constexpr int kStageBytes = 0;
@@ -616,12 +811,18 @@ struct EpiQkvRope {
     int seq_len;       // tokens per item (position = row % seq_len)
     const float* cos_tab;  // [seq_len, 16]
     const float* sin_tab;  // [seq_len, 16]
+    LnFold ln = LnFold{nullptr, nullptr, nullptr, 0.f, 0.f, 0};
   };
   __device__ static __forceinline__ void apply(const Params& p, const EpiCtx& c, const uint32_t (&r)[32]) {
     if (!c.valid) return;
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if constexpr (LN) {
+      const LnRow lr = ln_row(p.ln, c.row);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) ln_apply4(p.ln, lr, v[j], v[j + 1], v[j + 2], v[j + 3], c.col0 + j);
+    }
     // chunk of 32 columns aligned to 32: even chunks of a 64-wide head are the rotary dims
     if (c.col0 < p.rope_cols && ((c.col0 >> 5) & 1) == 0 && p.cos_tab) {
       const int pos = c.row % p.seq_len;
@@ -715,7 +916,7 @@ struct EpiHeadNorm16 {
 // half of the projection).  The weight rows are interleaved at load time so every
 // 64-column group holds 32 value columns followed by their 32 gate columns:
 //   out[row, g*32 + j] = (acc[g*64 + j] + b) * silu(acc[g*64 + 32 + j] + b')
-template <bool BF16>
+template <bool BF16, bool LN = false>
 struct EpiSwiglu {
   static constexpr int kCols = 64;
   static constexpr int kStageBytes = 0;
@@ -723,21 +924,52 @@ struct EpiSwiglu {
     void* out;
     int ld;             // inner dim (N/2)
     const float* bias;  // interleaved like the weight rows; may be null
+    LnFold ln = LnFold{nullptr, nullptr, nullptr, 0.f, 0.f, 0};
   };
   __device__ static __forceinline__ void apply(const Params& p, const EpiCtx& c, const uint32_t (&r)[64]) {
     if (!c.valid) return;
+    // four value columns and their four gate columns at a time, straight from the accumulator registers (a 64-float
+    // working copy next to the two 64-register chunk buffers of the epilogue loop spills)
     uint32_t o[16];
+    if constexpr (!LN) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float a0 = __uint_as_float(r[2 * j]), a1 = __uint_as_float(r[2 * j + 1]);
-      float g0 = __uint_as_float(r[32 + 2 * j]), g1 = __uint_as_float(r[33 + 2 * j]);
-      if (p.bias) {
-        a0 += __ldg(p.bias + c.col0 + 2 * j);
-        a1 += __ldg(p.bias + c.col0 + 2 * j + 1);
-        g0 += __ldg(p.bias + c.col0 + 32 + 2 * j);
-        g1 += __ldg(p.bias + c.col0 + 33 + 2 * j);
+      for (int j = 0; j < 16; ++j) {
+        float a0 = __uint_as_float(r[2 * j]), a1 = __uint_as_float(r[2 * j + 1]);
+        float g0 = __uint_as_float(r[32 + 2 * j]), g1 = __uint_as_float(r[33 + 2 * j]);
+        if (p.bias) {
+          a0 += __ldg(p.bias + c.col0 + 2 * j);
+          a1 += __ldg(p.bias + c.col0 + 2 * j + 1);
+          g0 += __ldg(p.bias + c.col0 + 32 + 2 * j);
+          g1 += __ldg(p.bias + c.col0 + 33 + 2 * j);
+        }
+        o[j] = Op16<BF16>::pack(a0 * silu_f(g0), a1 * silu_f(g1));
       }
-      o[j] = Op16<BF16>::pack(a0 * silu_f(g0), a1 * silu_f(g1));
+      uint4* dst0 =
+          reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + static_cast<size_t>(c.row) * p.ld + (c.col0 >> 1));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst0[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      return;
+    }
+    LnRow lr{1.f, 0.f};
+    if constexpr (LN) lr = ln_row(p.ln, c.row);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a0 = __uint_as_float(r[4 * j]), a1 = __uint_as_float(r[4 * j + 1]), a2 = __uint_as_float(r[4 * j + 2]),
+            a3 = __uint_as_float(r[4 * j + 3]);
+      float g0 = __uint_as_float(r[32 + 4 * j]), g1 = __uint_as_float(r[33 + 4 * j]), g2 = __uint_as_float(r[34 + 4 * j]),
+            g3 = __uint_as_float(r[35 + 4 * j]);
+      if constexpr (LN) {
+        ln_apply4(p.ln, lr, a0, a1, a2, a3, c.col0 + 4 * j);
+        ln_apply4(p.ln, lr, g0, g1, g2, g3, c.col0 + 32 + 4 * j);
+      }
+      if (p.bias) {
+        const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + c.col0 + 4 * j));
+        const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + c.col0 + 32 + 4 * j));
+        a0 += ba.x; a1 += ba.y; a2 += ba.z; a3 += ba.w;
+        g0 += bg.x; g1 += bg.y; g2 += bg.z; g3 += bg.w;
+      }
+      o[2 * j] = Op16<BF16>::pack(a0 * silu_f(g0), a1 * silu_f(g1));
+      o[2 * j + 1] = Op16<BF16>::pack(a2 * silu_f(g2), a3 * silu_f(g3));
     }
     uint4* dst =
         reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + static_cast<size_t>(c.row) * p.ld + (c.col0 >> 1));

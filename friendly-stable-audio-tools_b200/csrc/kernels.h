@@ -15,6 +15,7 @@ int debug_attention_occupancy(int dyn_smem, int carveout_pct);
 bool conv_halo_enabled();     // SATB_CONV_HALO=off: generic 7-tap loads for the final conv (A/B debugging)
 bool resunit_use_fused();      // SATB_RESUNIT=unfused runs the 128-channel ResidualUnits as two GEMM launches (A/B debugging)
 bool gemm_use_2cta();          // SATB_GEMM=1cta disables the CTA-pair GEMM (A/B debugging)
+bool ln_fold_enabled();        // SATB_LN=fold: LayerNorm folded into the GEMM epilogues (A/B; measured slower, off by default)
 bool raw_stream_16bit();       // SATB_RAW=fp32 keeps the Oobleck skip stream in fp32 (A/B debugging)
 
 // ---- elementwise.cu
@@ -22,6 +23,10 @@ bool raw_stream_16bit();       // SATB_RAW=fp32 keeps the Oobleck skip stream in
 int launch_layernorm(const float* x, const float* gamma, const float* beta, void* out16, int rows, int D,
                      const float* scale, const float* shift, int64_t mod_stride, int rows_per_item, int n_items,
                      bool bf16, cudaStream_t stream);
+// c[n] = sum_k W16[n,k] gamma[k], d[n] = sum_k W16[n,k] beta[k] (beta may be null -> d = 0): the per-column vectors of a
+// LayerNorm folded into the GEMM that follows it (gemm.cuh: LnFold)
+int launch_ln_fold_vectors(const void* w16, const float* gamma, const float* beta, float* c, float* d, int rows, int K,
+                           bool bf16, cudaStream_t stream);
 // Fused VDenoiser scaling + multistep sampler update + noise (see elementwise.cu).
 int launch_sampler_update(const float* x, const float* v, const float* d1, const float* d2, const float* nz, float* den,
                           float* x_next, float* x_in, long long n, float c_skip, float c_out, float A, float B, float C,

@@ -25,6 +25,19 @@ bool gemm_use_2cta() {
   return v == 1;
 }
 
+bool ln_fold_enabled() {
+  // Opt-in (SATB_LN=fold).  Measured on B200, SA-Open B=4: the fold removes the 1.0 ms / step of LayerNorm kernels but
+  // the heavier epilogues cost more than that (residual GEMMs +0.3 .. +0.4 ms each class, QKV +0.35 ms: they read h,
+  // write h + x16 + partial sums, and load the per-column vector c) - a net loss of ~0.4 ms / step, so the LayerNorm
+  // kernels stay the default (profiles/README.md).
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SATB_LN");
+    v = (e && std::string(e) == "fold") ? 1 : 0;
+  }
+  return v == 1;
+}
+
 bool raw_stream_16bit() {
   static int v = -1;
   if (v < 0) {

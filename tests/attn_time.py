@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.join(ROOT, "friendly-stable-audio-tools_b200"))
 import torch
 from stable_audio_tools import _native as nat
 
-B, H = 8, 24
+B, H = int(os.environ.get("ATTN_B", "8")), 24
 tag = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("SATB_"))
 for N in [int(a) for a in sys.argv[1:]] or [1025]:
     torch.manual_seed(0)
