@@ -50,6 +50,7 @@ constexpr int kRowBatch = 8;                                 // independent 16-b
 constexpr int kRowPathMax = 2;                               // Nq % 128 <= this: those rows take the row path
 constexpr int kAttnThreads = 384;                            // 4 control warps + 8 softmax warps
 constexpr int kSoftmaxThreads = 256;
+constexpr int kAttnPolyDefault = 0;                          // see SATB_ATTN_POLY
 constexpr int kExtraMax = 2;                                 // Nk % 128 <= this: those keys are added in the epilogue
 constexpr int kXRows = 16;                                   // rows of the leftover-key K / V tiles (TMA box)
 constexpr int kXBytes = kXRows * kD * 2;                     // 2 KB
@@ -120,6 +121,33 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
+}
+
+// 2^x for a pair on the FMA / ALU pipes instead of the SFU (x <= ~8; clamped at -126): round-to-nearest split
+// x = i + f, |f| <= 0.5 by the magic-number add, 2^f by its degree-4 Taylor polynomial (relative error < 4.2e-5, below
+// the 16-bit rounding P gets anyway), 2^i by an integer add into the exponent field.
+__device__ __forceinline__ void ex2_poly2(float x0, float x1, float& y0, float& y1) {
+  const float kMagic = 12582912.f;   // 1.5 * 2^23
+  x0 = fmaxf(x0, -126.f);
+  x1 = fmaxf(x1, -126.f);
+  const uint64_t x = pack2(x0, x1), mg = pack2(kMagic, kMagic), nmg = pack2(-kMagic, -kMagic);
+  const uint64_t t = fadd2(x, mg);                 // integer part in the low mantissa bits
+  uint64_t fi = fadd2(t, nmg);                     // float(i)
+  float f0, f1, i0, i1;
+  unpack2(fi, i0, i1);
+  const uint64_t f = fadd2(x, pack2(-i0, -i1));    // f = x - i
+  // Horner: ((((c4 f + c3) f + c2) f + c1) f + 1)
+  const float c1 = 0.6931471806f, c2 = 0.2402265070f, c3 = 0.0555041087f, c4 = 0.0096181291f;
+  uint64_t acc = ffma2(pack2(c4, c4), f, pack2(c3, c3));
+  acc = ffma2(acc, f, pack2(c2, c2));
+  acc = ffma2(acc, f, pack2(c1, c1));
+  acc = ffma2(acc, f, pack2(1.f, 1.f));
+  float t0, t1, p0, p1;
+  unpack2(t, t0, t1);
+  unpack2(acc, p0, p1);
+  (void)f0; (void)f1;
+  y0 = __uint_as_float(__float_as_uint(p0) + ((__float_as_uint(t0) - 0x4B400000u) << 23));
+  y1 = __uint_as_float(__float_as_uint(p1) + ((__float_as_uint(t1) - 0x4B400000u) << 23));
 }
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -248,7 +276,8 @@ __device__ void attn_row_path(const AttnTcArgs& p, int b, int h, int row, float*
   }
 }
 
-template <bool BF16>
+// POLY: every fourth pair of exponentials of a full chunk goes through ex2_poly2 (FMA / ALU pipes) instead of the SFU
+template <bool BF16, bool POLY>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKx,
@@ -526,7 +555,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             for (int e = 0; e < 16; ++e) {
               float t0, t1;
               unpack2(ffma2(pack2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), sc2, nm2), t0, t1);
-              const float p0 = ex2_approx(t0), p1 = ex2_approx(t1);
+              float p0, p1;
+              if (POLY && (e & 3) == 3) {
+                ex2_poly2(t0, t1, p0, p1);
+              } else {
+                p0 = ex2_approx(t0);
+                p1 = ex2_approx(t1);
+              }
               sum2 = fadd2(sum2, pack2(p0, p1));
               w[e] = Op16<BF16>::pack(p0, p1);
             }
@@ -797,32 +832,25 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
   const int slots = ctas_per_sm * device_sm_count();
   if (grid > slots) grid = slots;
   if (grid <= 0) return 0;
-  static PerDeviceOnce attr16, attrbf;
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = getenv("SATB_ATTN_POLY");        // 0 / 1: A-B of the FMA-pipe exponentials
+    poly = e ? (atoi(e) != 0) : kAttnPolyDefault;
+  }
   auto prepare = [&](auto kern) -> int {
     SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    // two CTAs per SM need 2 x 102 KB: ask for the largest shared-memory carveout
+    // two CTAs per SM need 2 x 98 KB: ask for the largest shared-memory carveout
     SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    if (getenv("SATB_ATTN_DEBUG")) {
-      int nb = -1, dev = 0, sm_smem = 0, rsv = 0, regs = 0;
-      cudaGetDevice(&dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kAttnThreads, kAttnSmem);
-      cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-      cudaDeviceGetAttribute(&rsv, cudaDevAttrReservedSharedMemoryPerBlock, dev);
-      cudaDeviceGetAttribute(&regs, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
-      cudaFuncAttributes fa;
-      cudaFuncGetAttributes(&fa, kern);
-      fprintf(stderr, "[satb] attention: %d resident CTAs per SM (dyn smem %d B + static %zu B per CTA, %d regs/thread; SM: "
-              "%d B smem, %d B reserved per block, %d regs)\n", nb, kAttnSmem, fa.sharedSizeBytes, fa.numRegs, sm_smem, rsv, regs);
-    }
     return 0;
   };
-  if (bf16) {
-    if (attrbf.first()) SATB_PROPAGATE(prepare(attn_tc_kernel<true>));
-    SATB_CHECK_CUDA(launch_pdl(attn_tc_kernel<true>, dim3(grid), dim3(kAttnThreads), kAttnSmem, stream, tq, tk, tv, tkx, tvx, a));
-  } else {
-    if (attr16.first()) SATB_PROPAGATE(prepare(attn_tc_kernel<false>));
-    SATB_CHECK_CUDA(launch_pdl(attn_tc_kernel<false>, dim3(grid), dim3(kAttnThreads), kAttnSmem, stream, tq, tk, tv, tkx, tvx, a));
-  }
+  auto go = [&](auto kern, PerDeviceOnce& once) -> int {
+    if (once.first()) SATB_PROPAGATE(prepare(kern));
+    SATB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kAttnThreads), kAttnSmem, stream, tq, tk, tv, tkx, tvx, a));
+    return 0;
+  };
+  static PerDeviceOnce o00, o01, o10, o11;
+  if (bf16) SATB_PROPAGATE(poly ? go(attn_tc_kernel<true, true>, o11) : go(attn_tc_kernel<true, false>, o10));
+  else SATB_PROPAGATE(poly ? go(attn_tc_kernel<false, true>, o01) : go(attn_tc_kernel<false, false>, o00));
   count_launch();
   SATB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -831,7 +859,7 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
 // Debug: resident CTAs per SM the runtime reports for the attention kernel with `dyn_smem` bytes of dynamic shared
 // memory and the given carveout preference (percent, -1 = leave unchanged); tests / profiling only.
 int debug_attention_occupancy(int dyn_smem, int carveout_pct) {
-  auto kern = attn_tc_kernel<false>;
+  auto kern = attn_tc_kernel<false, false>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem) != cudaSuccess) return -1;
   if (carveout_pct >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct);
   int nb = -1;
