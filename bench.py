@@ -409,6 +409,25 @@ def run_native(args):
         tmax = torch.tensor([decode_ms], device=device)
         td.all_reduce(tmax, op=td.ReduceOp.MAX)
         decode_ms = float(tmax.item())
+    # ---------------- the decoder at the reference's own precision (split-operand mode), for the record ---------------
+    dec_x3_ms = None
+    if world == 1 and args.config == 3:
+        from oracle import oobleck_oracle as oo
+        from stable_audio_tools.models.autoencoders import OobleckDecoder
+        dec3 = OobleckDecoder(**SAO_DEC, operand_dtype="fp16x3")
+        dec3.load_state_dict(oo.make_oobleck_weights(oo.decoder_param_shapes(SAO_DEC), seed=1,
+                                                     transposed=oo.decoder_transposed_prefixes(SAO_DEC)))
+        dec3 = dec3.to(device).eval()
+        dec3(lat[:1])
+        torch.cuda.synchronize()
+        x0_, x1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0_.record()
+        for _ in range(2):
+            dec3(lat[:1])
+        x1_.record()
+        torch.cuda.synchronize()
+        dec_x3_ms = x0_.elapsed_time(x1_) / 2
+        del dec3
     # ---------------- other BASELINE.json shapes, for the record (single GPU only) ---------------
     # configs[1]: one prompt (2 CFG rows x 1025 tokens); configs[4]: SA-2.0 length (L = 6144 latents, 1 prompt).
     extra_shapes = {}
@@ -500,6 +519,11 @@ def run_native(args):
                             "frac_of_hbm_peak_survey_denominator": survey_gb / (dec_ms_sample / 1e3) / hbm_peak,
                             "roofline_floor_ms": max(dec_flops / (peak_tf * 1e12), dec_bytes / (hbm_peak * 1e9)) * 1e3,
                             "byte_model": "profiles/tools/decoder_bytes.py",
+                            # operand_dtype="fp16x3": 3 MMAs per product, fp32 skip stream, ~60 dB instead of ~40 dB vs fp32
+                            "fp16x3_ms_per_sample": dec_x3_ms,
+                            "audio_sec_per_s_100step_fp16x3": (world * BATCH * AUDIO_SECONDS /
+                                                               ((GEN_STEPS * ms_per_step + BATCH * dec_x3_ms) / 1e3))
+                            if dec_x3_ms else None,
                             "note": "5.16 TFLOP per 1024 latents: with the 16-bit streams of this round the decoder's "
                                     "tensor time exceeds its HBM time, i.e. the bound is the tensor pipe"},
     }

@@ -37,6 +37,10 @@ struct GemmShape {
                     // addressed as (phase = u mod stride, row = u div stride) of the 4-D map
   int b_static = 0; // 1: B holds long-lived weights that no kernel still running can be writing, so its first
                     // tiles may be fetched before the programmatic-dependency wait
+  int n_parts = 1;  // 3: split-operand products for ~fp32 accuracy from 16-bit tensor-core operands: every tap is
+                    // issued three times into the same accumulator, (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo), where
+                    // x_lo = 16-bit(x - x_hi); A_lo comes through the second tensor map, W_lo sits b_part_rows below W_hi
+  int b_part_rows = 0;
 };
 
 constexpr int kBlockM = 128;
@@ -101,7 +105,7 @@ struct EpiTile {
 template <class Epi, int BN, bool BF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmShape s, const typename Epi::Params ep) {
+                    const __grid_constant__ CUtensorMap tmA2, const GemmShape s, const typename Epi::Params ep) {
   using Cfg = GemmCfg<BN, Epi::kStageBytes>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -120,7 +124,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int tiles_per_n = m_tiles * s.batches;
   const int total_tiles = tiles_per_n * n_tiles;
   const int kb_per_tap = (s.K + kBlockK - 1) / kBlockK;
-  const int num_kb = kb_per_tap * s.n_taps;
+  const int kb_per_part = kb_per_tap * s.n_taps;
+  const int num_kb = kb_per_part * s.n_parts;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -158,10 +163,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         pre = num_kb < Cfg::kStages ? num_kb : Cfg::kStages;
         const int n0 = (static_cast<int>(blockIdx.x) / tiles_per_n) * BN;
         for (int kb = 0; kb < pre; ++kb) {
-          const int tap = kb / kb_per_tap;
-          const int k0 = (kb - tap * kb_per_tap) * kBlockK;
+          const int part = kb / kb_per_part, kbp = kb - part * kb_per_part;
+          const int tap = kbp / kb_per_tap;
+          const int k0 = (kbp - tap * kb_per_tap) * kBlockK;
           mbar_expect_tx(&full_bar[kb], Cfg::kStage);
-          tma_load_2d(smem + kb * Cfg::kStage + Cfg::kStageA, &tmB, &full_bar[kb], k0, tap * s.b_tap_rows + n0);
+          tma_load_2d(smem + kb * Cfg::kStage + Cfg::kStageA, &tmB, &full_bar[kb], k0,
+                      tap * s.b_tap_rows + n0 + (part == 2 ? s.b_part_rows : 0));
         }
       }
       pdl_wait();
@@ -174,8 +181,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int m0 = (rem - batch * m_tiles) * kBlockM;
         const int n0 = nt * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / kb_per_tap;
-          const int k0 = (kb - tap * kb_per_tap) * kBlockK;
+          const int part = kb / kb_per_part, kbp = kb - part * kb_per_part;
+          const int tap = kbp / kb_per_tap;
+          const int k0 = (kbp - tap * kb_per_tap) * kBlockK;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStage;
           uint8_t* sb = sa + Cfg::kStageA;
@@ -187,8 +195,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ro = (u >= 0) ? u / s.stride : -((-u + s.stride - 1) / s.stride);   // floor division
             ph = u - ro * s.stride;
           }
-          tma_load_4d(sa, &tmA, &full_bar[stage], k0, ph, m0 + ro, batch);
-          if (!b_done) tma_load_2d(sb, &tmB, &full_bar[stage], k0, tap * s.b_tap_rows + n0);
+          tma_load_4d(sa, part == 1 ? &tmA2 : &tmA, &full_bar[stage], k0, ph, m0 + ro, batch);
+          if (!b_done)
+            tma_load_2d(sb, &tmB, &full_bar[stage], k0, tap * s.b_tap_rows + n0 + (part == 2 ? s.b_part_rows : 0));
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -330,7 +339,7 @@ struct Gemm2Cfg {
 template <class Epi, int BN, bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmShape s, const typename Epi::Params ep) {
+                         const __grid_constant__ CUtensorMap tmA2, const GemmShape s, const typename Epi::Params ep) {
   using Cfg = Gemm2Cfg<BN, Epi::kStageBytes>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -351,7 +360,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int tiles_per_n = m_tiles * s.batches;
   const int total_tiles = tiles_per_n * n_tiles;
   const int kb_per_tap = (s.K + kBlockK - 1) / kBlockK;
-  const int num_kb = kb_per_tap * s.n_taps;
+  const int kb_per_part = kb_per_tap * s.n_taps;
+  const int num_kb = kb_per_part * s.n_parts;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -386,10 +396,12 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         pre = num_kb < Cfg::kStages ? num_kb : Cfg::kStages;
         const int n0 = (cluster_id / tiles_per_n) * BN + rank * (BN / 2);
         for (int kb = 0; kb < pre; ++kb) {
-          const int tap = kb / kb_per_tap;
-          const int k0 = (kb - tap * kb_per_tap) * kBlockK;
+          const int part = kb / kb_per_part, kbp = kb - part * kb_per_part;
+          const int tap = kbp / kb_per_tap;
+          const int k0 = (kbp - tap * kb_per_tap) * kBlockK;
           if (rank == 0) mbar_expect_tx(&full_bar[kb], 2 * Cfg::kStage);
-          tma_load_2d_2sm(smem + kb * Cfg::kStage + Cfg::kStageA, &tmB, &full_bar[kb], k0, tap * s.b_tap_rows + n0);
+          tma_load_2d_2sm(smem + kb * Cfg::kStage + Cfg::kStageA, &tmB, &full_bar[kb], k0,
+                          tap * s.b_tap_rows + n0 + (part == 2 ? s.b_part_rows : 0));
         }
       }
       pdl_wait();
@@ -402,8 +414,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int m0 = (rem - batch * m_tiles) * 2 * kBlockM + rank * kBlockM;
         const int n0 = nt * BN + rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / kb_per_tap;
-          const int k0 = (kb - tap * kb_per_tap) * kBlockK;
+          const int part = kb / kb_per_part, kbp = kb - part * kb_per_part;
+          const int tap = kbp / kb_per_tap;
+          const int k0 = (kbp - tap * kb_per_tap) * kBlockK;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStage;
           uint8_t* sb = sa + Cfg::kStageA;
@@ -415,8 +428,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             ro = (u >= 0) ? u / s.stride : -((-u + s.stride - 1) / s.stride);
             ph = u - ro * s.stride;
           }
-          tma_load_4d_2sm(sa, &tmA, &full_bar[stage], k0, ph, m0 + ro, batch);
-          if (!b_done) tma_load_2d_2sm(sb, &tmB, &full_bar[stage], k0, tap * s.b_tap_rows + n0);
+          tma_load_4d_2sm(sa, part == 1 ? &tmA2 : &tmA, &full_bar[stage], k0, ph, m0 + ro, batch);
+          if (!b_done)
+            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], k0, tap * s.b_tap_rows + n0 + (part == 2 ? s.b_part_rows : 0));
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -1044,6 +1058,7 @@ struct EpiConv {
     int L_out;            // output positions per batch item
     int up;               // transposed-conv stride (1 = ordinary conv)
     int pad;              // transposed-conv padding
+    void* s16_lo_out;     // split-operand mode: 16-bit(y' - 16-bit(y')) next to s16_out (y' = the Snake-activated value), or null
     int raw16;            // 1: the raw (un-activated) stream is stored in the 16-bit operand type instead of fp32:
                           // 8 instead of 12 bytes per element and channel through a fused ResidualUnit (the sums
                           // are still formed in fp32; only the value carried to the next unit's skip is rounded)
@@ -1149,8 +1164,13 @@ struct EpiConv {
           float x0, x1, x2, x3;
           f2_unpack(v01, x0, x1);
           f2_unpack(v23, x2, x3);
-          *reinterpret_cast<uint2*>(static_cast<uint16_t*>(p.s16_out) + idx) =
-              make_uint2(Op16<BF16>::pack(x0, x1), Op16<BF16>::pack(x2, x3));
+          const uint32_t h01 = Op16<BF16>::pack(x0, x1), h23 = Op16<BF16>::pack(x2, x3);
+          *reinterpret_cast<uint2*>(static_cast<uint16_t*>(p.s16_out) + idx) = make_uint2(h01, h23);
+          if (p.s16_lo_out) {
+            const float2 a = Op16<BF16>::unpack(h01), b = Op16<BF16>::unpack(h23);
+            *reinterpret_cast<uint2*>(static_cast<uint16_t*>(p.s16_lo_out) + idx) =
+                make_uint2(Op16<BF16>::pack(x0 - a.x, x1 - a.y), Op16<BF16>::pack(x2 - b.x, x3 - b.y));
+          }
         }
       }
     }
@@ -1197,7 +1217,7 @@ int make_tmap_b(CUtensorMap* m, const void* ptr, int K, int rows, int64_t row_st
 
 template <class Epi, int BN, bool BF16>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const typename Epi::Params& ep,
-                cudaStream_t stream) {
+                cudaStream_t stream, const CUtensorMap* tmA2 = nullptr) {
   using Cfg = GemmCfg<BN, Epi::kStageBytes>;
   auto kern = gemm_tcgen05_kernel<Epi, BN, BF16>;
   static PerDeviceOnce attr;
@@ -1207,14 +1227,15 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape&
   if (total <= 0) return 0;
   int grid = device_sm_count();
   if (grid > total) grid = total;
-  SATB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tmA, tmB, s, ep));
+  SATB_REQUIRE(s.n_parts == 1 || tmA2 != nullptr, "split-operand GEMM needs the second A tensor map");
+  SATB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tmA, tmB, tmA2 ? *tmA2 : tmA, s, ep));
   count_launch();
   return 0;
 }
 
 template <class Epi, int BN, bool BF16>
 int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const typename Epi::Params& ep,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, const CUtensorMap* tmA2 = nullptr) {
   using Cfg = Gemm2Cfg<BN, Epi::kStageBytes>;
   auto kern = gemm_tcgen05_2cta_kernel<Epi, BN, BF16>;
   static PerDeviceOnce attr;
@@ -1224,7 +1245,9 @@ int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmS
   if (total <= 0) return 0;
   int clusters = device_sm_count() / 2;
   if (clusters > total) clusters = total;
-  SATB_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tmA, tmB, s, ep));
+  SATB_REQUIRE(s.n_parts == 1 || tmA2 != nullptr, "split-operand GEMM needs the second A tensor map");
+  SATB_CHECK_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tmA, tmB,
+                             tmA2 ? *tmA2 : tmA, s, ep));
   count_launch();
   return 0;
 }

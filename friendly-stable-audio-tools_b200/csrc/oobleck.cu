@@ -53,8 +53,8 @@ __global__ void wn_scale_kernel(const float* __restrict__ g, const float* __rest
 //   mode 1: ConvT1d v [cin, cout, 2*up]    -> dst[tap][ph*cout+co][ci]  = v[ci, co, ph + tap*up] * scale[ci]
 template <bool BF16>
 __global__ void conv_w_prep_kernel(const float* __restrict__ v, const float* __restrict__ scale,
-                                   uint16_t* __restrict__ dst, int mode, int cin, int cout, int kk, int up,
-                                   size_t total) {
+                                   uint16_t* __restrict__ dst, uint16_t* __restrict__ dst_lo, int mode, int cin, int cout,
+                                   int kk, int up, size_t total) {
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int ci = static_cast<int>(i % cin);
@@ -72,6 +72,10 @@ __global__ void conv_w_prep_kernel(const float* __restrict__ v, const float* __r
     }
     typename Op16<BF16>::T h = Op16<BF16>::from_float(w);
     dst[i] = *reinterpret_cast<uint16_t*>(&h);
+    if (dst_lo) {   // split-operand mode: the part of w the 16-bit value lost
+      typename Op16<BF16>::T l = Op16<BF16>::from_float(w - Op16<BF16>::to_float(h));
+      dst_lo[i] = *reinterpret_cast<uint16_t*>(&l);
+    }
   }
 }
 
@@ -92,8 +96,8 @@ __global__ void snake_prep_kernel(const float* __restrict__ alpha, const float* 
 
 // NCL fp32 -> channels-last 16-bit (no activation): the decoder's latent input.
 template <bool BF16>
-__global__ void __launch_bounds__(256) ncl_to_nlc16_kernel(const float* __restrict__ x, uint16_t* __restrict__ y, int C,
-                                                           int L) {
+__global__ void __launch_bounds__(256) ncl_to_nlc16_kernel(const float* __restrict__ x, uint16_t* __restrict__ y,
+                                                           uint16_t* __restrict__ y_lo, int C, int L) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -109,6 +113,10 @@ __global__ void __launch_bounds__(256) ncl_to_nlc16_kernel(const float* __restri
     if (l < L && c < C) {
       typename Op16<BF16>::T h = Op16<BF16>::from_float(tile[tx][j]);
       y[(static_cast<size_t>(b) * L + l) * C + c] = *reinterpret_cast<uint16_t*>(&h);
+      if (y_lo) {
+        typename Op16<BF16>::T lo = Op16<BF16>::from_float(tile[tx][j] - Op16<BF16>::to_float(h));
+        y_lo[(static_cast<size_t>(b) * L + l) * C + c] = *reinterpret_cast<uint16_t*>(&lo);
+      }
     }
   }
 }
@@ -120,8 +128,8 @@ template <bool BF16>
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ audio, const float* __restrict__ w,
                                                       const float* __restrict__ bias, const float* __restrict__ sn_a,
                                                       const float* __restrict__ sn_ib, void* __restrict__ raw,
-                                                      uint16_t* __restrict__ s16, int Cin, int C, int64_t T, int kk,
-                                                      int raw16) {
+                                                      uint16_t* __restrict__ s16, uint16_t* __restrict__ s16_lo, int Cin,
+                                                      int C, int64_t T, int kk, int raw16) {
   constexpr int kTile = 64;
   extern __shared__ float sm_in[];  // [Cin][kTile + kk - 1]
   const int b = blockIdx.y;
@@ -151,8 +159,13 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
       } else {
         static_cast<float*>(raw)[o] = acc;
       }
-      typename Op16<BF16>::T h = Op16<BF16>::from_float(snake_fast(acc, a, ib));
+      const float act = snake_fast(acc, a, ib);
+      typename Op16<BF16>::T h = Op16<BF16>::from_float(act);
       s16[o] = *reinterpret_cast<uint16_t*>(&h);
+      if (s16_lo) {
+        typename Op16<BF16>::T lo = Op16<BF16>::from_float(act - Op16<BF16>::to_float(h));
+        s16_lo[o] = *reinterpret_cast<uint16_t*>(&lo);
+      }
     }
   }
 }
@@ -181,6 +194,8 @@ struct SatbOobleck {
   SatbOobleckConfig cfg;
   bool bf16 = false;
   int raw16 = 0;                   // 1: the raw skip stream is carried in the 16-bit operand type (fp16 mode), 0: fp32
+  bool split3 = false;             // operand_dtype 2 ("fp16x3"): every product as (hi, hi) + (lo, hi) + (hi, lo), see GemmShape
+  size_t lo_off = 0;               // bytes from a 16-bit activation buffer to its "lo" half (split3)
   std::vector<int> chans;          // c_mults[i] * channels, i = 0..n (c_mults prepended with 1)
   std::map<std::string, std::pair<float*, long long>> raw;   // state-dict entries (device fp32)
   std::vector<void*> owned;
@@ -253,14 +268,16 @@ int prep_conv(SatbOobleck* h, const std::string& pfx, int cin, int cout, int k, 
     SATB_PROPAGATE(h->alloc_bytes(reinterpret_cast<void**>(&c.w32), total * 4));
     fold_small_kernel<<<static_cast<int>(ceil_div64(total, 256)), 256, 0, st>>>(v, scale, c.w32, slice, total);
   } else {
-    SATB_PROPAGATE(h->alloc_bytes(reinterpret_cast<void**>(&c.w16), total * 2 + 256 * 128));  // slack for box overreach
-    SATB_CHECK_CUDA(cudaMemsetAsync(c.w16, 0, total * 2 + 256 * 128, st));
+    const size_t parts = h->split3 ? 2 : 1;      // [hi block | lo block]
+    SATB_PROPAGATE(h->alloc_bytes(reinterpret_cast<void**>(&c.w16), parts * total * 2 + 256 * 128));  // slack for box overreach
+    SATB_CHECK_CUDA(cudaMemsetAsync(c.w16, 0, parts * total * 2 + 256 * 128, st));
+    uint16_t* w_lo = h->split3 ? c.w16 + total : nullptr;
     int grid = static_cast<int>(ceil_div64(total, 256));
     if (grid > 8192) grid = 8192;
     if (h->bf16)
-      conv_w_prep_kernel<true><<<grid, 256, 0, st>>>(v, scale, c.w16, transposed ? 1 : 0, cin, cout, k, up, total);
+      conv_w_prep_kernel<true><<<grid, 256, 0, st>>>(v, scale, c.w16, w_lo, transposed ? 1 : 0, cin, cout, k, up, total);
     else
-      conv_w_prep_kernel<false><<<grid, 256, 0, st>>>(v, scale, c.w16, transposed ? 1 : 0, cin, cout, k, up, total);
+      conv_w_prep_kernel<false><<<grid, 256, 0, st>>>(v, scale, c.w16, w_lo, transposed ? 1 : 0, cin, cout, k, up, total);
   }
   count_launch();
   SATB_CHECK_CUDA(cudaGetLastError());
@@ -336,24 +353,31 @@ int run_conv_gemm(SatbOobleck* h, const ConvW& cw, const void* in16, int B, int 
   const CUtensorMap* tap;
   SATB_PROPAGATE(get_tmap_a(h, in16, cw.cin, a_rows, B, L_in, a_stride, &tap));
   const CUtensorMap& ta = *tap;
-  const int b_rows = s.n_taps * s.b_tap_rows;
+  const CUtensorMap* ta2 = nullptr;
+  int b_rows = s.n_taps * s.b_tap_rows;
+  if (h->split3) {
+    SATB_PROPAGATE(get_tmap_a(h, static_cast<const char*>(in16) + h->lo_off, cw.cin, a_rows, B, L_in, a_stride, &ta2));
+    s.n_parts = 3;
+    s.b_part_rows = b_rows;       // the lo weight block follows the hi block
+    b_rows *= 2;
+  }
   auto get_b = [&](int box, const CUtensorMap** out) -> int { return get_tmap_b(h, cw, b_rows, box, out); };
   const CUtensorMap* tb;
   if (s.N >= 256 && s.L >= 512 && gemm_use_2cta()) {
     SATB_PROPAGATE(get_b(128, &tb));   // CTA pair: each CTA loads half of the 256-wide B tile
-    return launch_gemm_2cta<Epi, 256, BF16>(ta, *tb, s, ep, st);
+    return launch_gemm_2cta<Epi, 256, BF16>(ta, *tb, s, ep, st, ta2);
   } else if (s.N >= 256) {
     SATB_PROPAGATE(get_b(256, &tb));
-    return launch_gemm<Epi, 256, BF16>(ta, *tb, s, ep, st);
+    return launch_gemm<Epi, 256, BF16>(ta, *tb, s, ep, st, ta2);
   } else if (s.N == 128 && s.L >= 512 && gemm_use_2cta()) {
     SATB_PROPAGATE(get_b(64, &tb));    // CTA pair on 256 x 128 tiles: halves the B traffic of the 128-channel layers
-    return launch_gemm_2cta<Epi, 128, BF16>(ta, *tb, s, ep, st);
+    return launch_gemm_2cta<Epi, 128, BF16>(ta, *tb, s, ep, st, ta2);
   } else if (s.N > 64) {
     SATB_PROPAGATE(get_b(128, &tb));
-    return launch_gemm<Epi, 128, BF16>(ta, *tb, s, ep, st);
+    return launch_gemm<Epi, 128, BF16>(ta, *tb, s, ep, st, ta2);
   }
   SATB_PROPAGATE(get_b(64, &tb));
-  return launch_gemm<Epi, 64, BF16>(ta, *tb, s, ep, st);
+  return launch_gemm<Epi, 64, BF16>(ta, *tb, s, ep, st, ta2);
 }
 
 // ResidualUnit (models/autoencoders.py:45-68).  In: snake1(x) as 16-bit in sA, x as fp32 in raw.
@@ -367,9 +391,9 @@ int residual_unit(SatbOobleck* h, const std::string& pfx, int C, int B, int L, i
   const SnakeW& s2 = h->snakes.at(pfx + "layers.2.");
   typedef EpiConv<BF16> E;
   typename E::Params e1{c1.bias, raw, keep_raw ? raw : nullptr, sA, next_snake ? next_snake->a : nullptr,
-                        next_snake ? next_snake->ib : nullptr, C, L, 1, 0, h->raw16};
+                        next_snake ? next_snake->ib : nullptr, C, L, 1, 0, h->split3 ? static_cast<char*>(sA) + h->lo_off : nullptr, h->raw16};
   if (C == ResUnitCfg::kC && c7.k == ResUnitCfg::kTaps && dil <= ResUnitCfg::kMaxDil && L >= 512 && gemm_use_2cta() &&
-      resunit_use_fused()) {
+      resunit_use_fused() && !h->split3) {
     // one kernel: conv7 -> snake2 -> conv1 -> + skip; reads sA (with a halo), so it must write elsewhere
     const CUtensorMap *ta, *tb7, *tb1;
     SATB_PROPAGATE(get_tmap_a(h, sA, C, L, B, L, 1, &ta, ResUnitCfg::halo_rows(dil)));   // one halo box per k-block
@@ -383,7 +407,7 @@ int residual_unit(SatbOobleck* h, const std::string& pfx, int C, int B, int L, i
     return 0;
   }
   if (C == ResUnit256Cfg::kC && c7.k == ResUnit256Cfg::kTaps && dil <= ResUnit256Cfg::kMaxDil && L >= 512 &&
-      gemm_use_2cta() && resunit_use_fused()) {
+      gemm_use_2cta() && resunit_use_fused() && !h->split3) {
     const CUtensorMap *ta, *tb7, *tb1;
     SATB_PROPAGATE(get_tmap_a(h, sA, C, L, B, L, 1, &ta, ResUnit256Cfg::halo_rows(dil)));
     SATB_PROPAGATE(get_tmap_b(h, c7, c7.k * C, 128, &tb7));
@@ -396,7 +420,7 @@ int residual_unit(SatbOobleck* h, const std::string& pfx, int C, int B, int L, i
     return 0;
   }
   // conv7(dil) on sA -> snake2 -> sT ; conv1 on sT -> + x -> raw, snake_next -> sA
-  typename E::Params e7{c7.bias, nullptr, nullptr, sT, s2.a, s2.ib, C, L, 1, 0, h->raw16};
+  typename E::Params e7{c7.bias, nullptr, nullptr, sT, s2.a, s2.ib, C, L, 1, 0, h->split3 ? static_cast<char*>(sT) + h->lo_off : nullptr, h->raw16};
   SATB_PROPAGATE((run_conv_gemm<E, BF16>(h, c7, sA, B, L, 0, dil, 1, e7, st)));
   SATB_PROPAGATE((run_conv_gemm<E, BF16>(h, c1, sT, B, L, 0, 1, 1, e1, st)));
   return 0;
@@ -417,8 +441,9 @@ int decode_impl(SatbOobleck* h, const float* z, float* audio, int B, int L, cuda
     }
   }
   SATB_PROPAGATE(h->ensure(&h->buf_raw, &h->cap_raw, max_elems * 4));
-  SATB_PROPAGATE(h->ensure(&h->buf_a, &h->cap_a, max_elems * 2));
-  SATB_PROPAGATE(h->ensure(&h->buf_b, &h->cap_b, max_elems * 2));
+  h->lo_off = h->split3 ? ((max_elems * 2 + 255) & ~static_cast<size_t>(255)) : 0;   // [hi | lo] halves of sA / sB
+  SATB_PROPAGATE(h->ensure(&h->buf_a, &h->cap_a, max_elems * 2 + h->lo_off));
+  SATB_PROPAGATE(h->ensure(&h->buf_b, &h->cap_b, max_elems * 2 + h->lo_off));
   void* raw = h->buf_raw;
   void* sA = h->buf_a;
   void* sB = h->buf_b;
@@ -426,14 +451,16 @@ int decode_impl(SatbOobleck* h, const float* z, float* audio, int B, int L, cuda
   // latent NCL fp32 -> channels-last 16-bit
   {
     dim3 grid(ceil_div(L, 32), ceil_div(c.latent_dim, 32), B);
-    ncl_to_nlc16_kernel<BF16><<<grid, 256, 0, st>>>(z, static_cast<uint16_t*>(sB), c.latent_dim, L);
+    ncl_to_nlc16_kernel<BF16><<<grid, 256, 0, st>>>(z, static_cast<uint16_t*>(sB),
+                                                    h->split3 ? reinterpret_cast<uint16_t*>(static_cast<char*>(sB) + h->lo_off) : nullptr,
+                                                    c.latent_dim, L);
     count_launch();
   }
   // layers.0: conv k7 latent -> chans[n]; epilogue applies block 1's leading Snake
   {
     const ConvW& c0 = h->convs.at("layers.0.");
     const SnakeW& sn = h->snakes.at("layers.1.layers.0.");
-    typename E::Params ep{c0.bias, nullptr, nullptr, sA, sn.a, sn.ib, c0.cout, L, 1, 0, h->raw16};
+    typename E::Params ep{c0.bias, nullptr, nullptr, sA, sn.a, sn.ib, c0.cout, L, 1, 0, h->split3 ? static_cast<char*>(sA) + h->lo_off : nullptr, h->raw16};
     SATB_PROPAGATE((run_conv_gemm<E, BF16>(h, c0, sB, B, L, 0, 1, 1, ep, st)));
   }
   int64_t Lc = L;
@@ -445,7 +472,7 @@ int decode_impl(SatbOobleck* h, const float* z, float* audio, int B, int L, cuda
     const int64_t Lo = Lc * s;
     SATB_REQUIRE(Lo < (int64_t(1) << 31) && static_cast<int64_t>(B) * Lo * cout < (int64_t(1) << 40), "decoder: sequence too long");
     // transposed conv reads sA [B, Lc, cin], writes raw + snake(ru0) into sB
-    typename E::Params et{ct.bias, nullptr, raw, sB, s_ru0.a, s_ru0.ib, cout, static_cast<int>(Lo), s, (s + 1) / 2, h->raw16};
+    typename E::Params et{ct.bias, nullptr, raw, sB, s_ru0.a, s_ru0.ib, cout, static_cast<int>(Lo), s, (s + 1) / 2, h->split3 ? static_cast<char*>(sB) + h->lo_off : nullptr, h->raw16};
     SATB_PROPAGATE((run_conv_gemm<E, BF16>(h, ct, sA, B, static_cast<int>(Lc), 1, 1, s, et, st)));
     std::swap(sA, sB);  // sA now holds the residual units' input
     for (int j = 0; j < 3; ++j) {
@@ -470,7 +497,7 @@ int decode_impl(SatbOobleck* h, const float* z, float* audio, int B, int L, cuda
     const ConvW& cf = h->convs.at("layers." + std::to_string(n + 2) + ".");
     EpiStoreNCL::Params ep{audio, nullptr, cf.cout, static_cast<int>(Lc), c.final_tanh};
     ConvHaloShape hs{static_cast<int>(Lc), B, cf.cin, cf.k, 1, cf.cout};
-    if (conv_halo_enabled() && cf.cout <= ConvHaloCfg::kBN && cf.cin % kBlockK == 0 && cf.cin <= 256 &&
+    if (conv_halo_enabled() && !h->split3 && cf.cout <= ConvHaloCfg::kBN && cf.cin % kBlockK == 0 && cf.cin <= 256 &&
         ConvHaloCfg::halo_rows(hs) <= 256) {
       // every activation row is fetched once per tile instead of once per tap (see conv_halo.cuh)
       const CUtensorMap *ta, *tb;
@@ -502,8 +529,9 @@ int encode_impl(SatbOobleck* h, const float* audio, float* latents, int B, int64
     }
   }
   SATB_PROPAGATE(h->ensure(&h->buf_raw, &h->cap_raw, max_elems * 4));
-  SATB_PROPAGATE(h->ensure(&h->buf_a, &h->cap_a, max_elems * 2));
-  SATB_PROPAGATE(h->ensure(&h->buf_b, &h->cap_b, max_elems * 2));
+  h->lo_off = h->split3 ? ((max_elems * 2 + 255) & ~static_cast<size_t>(255)) : 0;   // [hi | lo] halves of sA / sB
+  SATB_PROPAGATE(h->ensure(&h->buf_a, &h->cap_a, max_elems * 2 + h->lo_off));
+  SATB_PROPAGATE(h->ensure(&h->buf_b, &h->cap_b, max_elems * 2 + h->lo_off));
   void* raw = h->buf_raw;
   void* sA = h->buf_a;
   void* sB = h->buf_b;
@@ -516,6 +544,7 @@ int encode_impl(SatbOobleck* h, const float* audio, float* latents, int B, int64
     const size_t smem = static_cast<size_t>(c0.cin) * (64 + c0.k - 1) * 4;
     dim3 grid(static_cast<unsigned>(ceil_div64(T, 64)), B);
     conv_in_kernel<BF16><<<grid, 256, smem, st>>>(audio, c0.w32, c0.bias, sn.a, sn.ib, raw, static_cast<uint16_t*>(sA),
+                                                   h->split3 ? reinterpret_cast<uint16_t*>(static_cast<char*>(sA) + h->lo_off) : nullptr,
                                                    c0.cin, c0.cout, T, c0.k, h->raw16);
     count_launch();
   }
@@ -535,7 +564,7 @@ int encode_impl(SatbOobleck* h, const float* audio, float* latents, int B, int64
     const int64_t Lo = Lc / s;
     const SnakeW* nx = b < n ? &h->snakes.at("layers." + std::to_string(b + 1) + ".layers.0.layers.0.")
                              : &h->snakes.at("layers." + std::to_string(n + 1) + ".");
-    typename E::Params ep{cs.bias, nullptr, b < n ? raw : nullptr, sB, nx->a, nx->ib, cs.cout, static_cast<int>(Lo), 1, 0, h->raw16};
+    typename E::Params ep{cs.bias, nullptr, b < n ? raw : nullptr, sB, nx->a, nx->ib, cs.cout, static_cast<int>(Lo), 1, 0, h->split3 ? static_cast<char*>(sB) + h->lo_off : nullptr, h->raw16};
     SATB_PROPAGATE((run_conv_gemm<E, BF16>(h, cs, sA, B, static_cast<int>(Lc), 2, 1, s, ep, st)));
     std::swap(sA, sB);
     Lc = Lo;
@@ -562,10 +591,11 @@ int satb_oobleck_create(const SatbOobleckConfig* cfg, SatbOobleck** out) {
   SatbOobleck* h = new SatbOobleck();
   h->cfg = *cfg;
   h->bf16 = cfg->operand_dtype == 1;
+  h->split3 = cfg->operand_dtype == 2;
   // fp16 operands: the un-activated skip stream is carried in fp16 as well (8 instead of 12 bytes per element and
   // channel through a fused ResidualUnit; measured +23 % on the fp16-operand error floor, tests/test_gpu_baseline_size).
   // bf16 (8 mantissa bits) keeps the fp32 stream.  SATB_RAW=fp32 restores fp32 for A/B measurements.
-  h->raw16 = (!h->bf16 && raw_stream_16bit()) ? 1 : 0;
+  h->raw16 = (!h->bf16 && !h->split3 && raw_stream_16bit()) ? 1 : 0;
   h->chans.push_back(cfg->channels);
   for (int i = 0; i < cfg->n_stages; ++i) h->chans.push_back(cfg->c_mults[i] * cfg->channels);
   *out = h;

@@ -130,7 +130,12 @@ class _NativeOobleck(nn.Module):
                 cfg.c_mults[i], cfg.strides[i] = m, s
             cfg.final_tanh = int(nc["final_tanh"])
             cfg.is_decoder = int(self._is_decoder)
-            cfg.operand_dtype = 1 if nc["operand_dtype"] == "bf16" else 0
+            # "fp16" (default) | "bf16" | "fp16x3": split-operand mode, every conv product as (hi, hi) + (lo, hi) + (hi, lo)
+            # with x_lo = fp16(x - x_hi): ~fp32 accuracy (the reference runs these convolutions in strict fp32,
+            # inference/generation.py:165-166) at ~3x the tensor-core work
+            if nc["operand_dtype"] not in ("fp16", "bf16", "fp16x3"):
+                raise ValueError(f"operand_dtype must be fp16, bf16 or fp16x3, got {nc['operand_dtype']}")
+            cfg.operand_dtype = {"fp16": 0, "bf16": 1, "fp16x3": 2}[nc["operand_dtype"]]
             h = ctypes.c_void_p()
             _native.check(lib.satb_oobleck_create(ctypes.byref(cfg), ctypes.byref(h)))
             self.__dict__["_h"] = h

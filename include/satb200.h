@@ -54,7 +54,8 @@ typedef struct SatbOobleckConfig {
   int strides[SATB_MAX_STAGES];
   int final_tanh;           /* decoder only */
   int is_decoder;           /* 1 = OobleckDecoder, 0 = OobleckEncoder */
-  int operand_dtype;        /* 0 = fp16, 1 = bf16 (conv operands; accumulation is fp32) */
+  int operand_dtype;        /* 0 = fp16, 1 = bf16 (conv operands; accumulation is fp32), 2 = fp16 split hi + lo:
+                             * three MMAs per product, ~fp32 accuracy (the reference's own precision for this path) */
 } SatbOobleckConfig;
 
 /* ---- library ---------------------------------------------------------------------- */

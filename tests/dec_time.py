@@ -12,7 +12,7 @@ from stable_audio_tools.models.autoencoders import OobleckDecoder
 
 dcfg = dict(out_channels=2, channels=128, c_mults=[1, 2, 4, 8, 16], strides=[2, 4, 4, 8, 8], latent_dim=64,
             use_snake=True, final_tanh=False)
-dec = OobleckDecoder(**dcfg)
+dec = OobleckDecoder(**dcfg, operand_dtype=os.environ.get("DEC_DTYPE", "fp16"))
 dec.load_state_dict(oo.make_oobleck_weights(oo.decoder_param_shapes(dcfg), seed=9,
                                             transposed=oo.decoder_transposed_prefixes(dcfg)))
 dec = dec.cuda().eval()
@@ -49,5 +49,5 @@ r1.record()
 torch.cuda.synchronize()
 copy_gbs = 10 * 2 * (1 << 30) / (r0.elapsed_time(r1) / 1e3) / 1e9
 print("box: cublas bf16 %.0f TF/s, copy %.0f GB/s" % (gemm_tf, copy_gbs))
-tag = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("SATB_"))
+tag = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("SATB_") or k == "DEC_DTYPE")
 print("decode_ms %.3f  [%s]" % (e0.elapsed_time(e1) / reps, tag), flush=True)

