@@ -124,10 +124,14 @@ using namespace satb;
 
 struct SatbDit {
   SatbDitConfig cfg;
-  int D, H, dh, C, ct, ce, gd, ge, ffi, depth, F, nf;
+  int D, H, dh, C, Cin, ct, ce, gd, ge, ffi, depth, F, nf;   // C = output channels, Cin = C + input_concat_dim
+  int pdim = 0;               // prepend_cond_dim
+  float *pe0_w = nullptr, *pe2_w = nullptr;   // to_prepend_embed (fp32, bias-free)
+  int Pp = 0;                 // prepend-conditioning tokens of the current conditioning
+  DevBuf ws_prep;             // their embeddings [B, Pp, D] + scratch
   bool bf16, adaln, qk_norm = false;
   bool ln_fused = false;   // prepend-mode blocks without qk_norm: no LayerNorm kernels (see dit_forward_impl)
-  int P;  // prepended tokens (1 in "prepend" mode, 0 in adaLN mode)
+  int P;  // prepended tokens: 1 (the global-conditioning token; 0 in adaLN mode) + Pp
   std::vector<LayerW> layers;
   std::vector<void*> owned;   // every cudaMalloc of weight storage
   // globals
@@ -147,7 +151,7 @@ struct SatbDit {
   TmapCache tmaps;
   DevBuf ws_h, ws_a16, ws_qkv, ws_attn, ws_q16, ws_ff, ws_ain, ws_y, ws_small, ws_cond, ws_kv, ws_rope, ws_stats;
   int rope_len = 0;
-  int res_R = 0, res_L = 0;
+  int res_R = 0, res_L = 0, res_P = -1;
   // optional per-category CUDA-event timing (bench.py roofline)
   bool prof_on = false;
   struct ProfRec { int cat; cudaEvent_t a, b; };
@@ -191,12 +195,18 @@ int satb_dit_create(const SatbDitConfig* cfg, SatbDit** out) {
                "head dim must be 64");
   SATB_REQUIRE(cfg->io_channels % 8 == 0 && cfg->io_channels % 32 == 0, "io_channels must be a multiple of 32");
   SATB_REQUIRE(cfg->patch_size == 1, "patch_size 1 only");
+  SATB_REQUIRE(cfg->input_concat_dim >= 0 && cfg->input_concat_dim % 8 == 0, "input_concat_dim must be a multiple of 8");
+  SATB_REQUIRE(cfg->prepend_cond_dim >= 0 && cfg->prepend_cond_dim % 4 == 0, "prepend_cond_dim must be a multiple of 4");
+  SATB_REQUIRE(!(cfg->prepend_cond_dim > 0 && cfg->global_cond_type == 1),
+               "prepend conditioning is supported with global_cond_type \"prepend\" only");
   SatbDit* d = new SatbDit();
   d->cfg = *cfg;
   d->D = cfg->embed_dim;
   d->H = cfg->num_heads;
   d->dh = d->D / d->H;
   d->C = cfg->io_channels;
+  d->Cin = cfg->io_channels + (cfg->input_concat_dim > 0 ? cfg->input_concat_dim : 0);
+  d->pdim = cfg->prepend_cond_dim > 0 ? cfg->prepend_cond_dim : 0;
   d->ct = cfg->cond_token_dim;
   d->ce = cfg->project_cond_tokens ? d->D : d->ct;
   d->gd = cfg->global_cond_dim;
@@ -233,7 +243,7 @@ void satb_dit_destroy(SatbDit* d) {
   for (void* p : d->owned) cudaFree(p);
   d->ws_h.release(); d->ws_a16.release(); d->ws_qkv.release(); d->ws_attn.release(); d->ws_q16.release();
   d->ws_ff.release(); d->ws_ain.release(); d->ws_y.release(); d->ws_small.release(); d->ws_cond.release();
-  d->ws_kv.release(); d->ws_rope.release(); d->ws_stats.release();
+  d->ws_kv.release(); d->ws_rope.release(); d->ws_stats.release(); d->ws_prep.release();
   delete d;
 }
 
@@ -244,7 +254,7 @@ int satb_dit_load_weight(SatbDit* d, const char* name_c, const float* src, long 
   SATB_REQUIRE(d && name_c && src, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream_v);
   const std::string name(name_c);
-  const int D = d->D, C = d->C;
+  const int D = d->D, C = d->C, Cin = d->Cin;
   auto copy_f32 = [&](float** dst, long long expect) -> int {
     SATB_REQUIRE(numel == expect, ("bad size for " + name).c_str());
     if (!*dst) SATB_PROPAGATE(d->alloc(dst, expect));
@@ -267,9 +277,11 @@ int satb_dit_load_weight(SatbDit* d, const char* name_c, const float* src, long 
   if (name == "to_cond_embed.2.weight") return cast16(&d->ce2_w, d->ce, d->ce, nullptr);
   if (name == "to_global_embed.0.weight") return copy_f32(&d->ge0_w, static_cast<long long>(d->ge) * d->gd);
   if (name == "to_global_embed.2.weight") return copy_f32(&d->ge2_w, static_cast<long long>(d->ge) * d->ge);
-  if (name == "preprocess_conv.weight") return copy_f32(&d->pre_w, static_cast<long long>(C) * C);
+  if (name == "preprocess_conv.weight") return copy_f32(&d->pre_w, static_cast<long long>(Cin) * Cin);
+  if (name == "to_prepend_embed.0.weight" && d->pdim > 0) return copy_f32(&d->pe0_w, static_cast<long long>(D) * d->pdim);
+  if (name == "to_prepend_embed.2.weight" && d->pdim > 0) return copy_f32(&d->pe2_w, static_cast<long long>(D) * D);
   if (name == "postprocess_conv.weight") return copy_f32(&d->post_w, static_cast<long long>(C) * C);
-  if (name == "transformer.project_in.weight") return copy_f32(&d->pin_w, static_cast<long long>(D) * C);
+  if (name == "transformer.project_in.weight") return copy_f32(&d->pin_w, static_cast<long long>(D) * Cin);
   if (name == "transformer.project_out.weight") return copy_f32(&d->pout_w, static_cast<long long>(C) * D);
   if (name == "transformer.rotary_pos_emb.inv_freq") return copy_f32(&d->inv_freq, d->nf);
   const std::string lp = "transformer.layers.";
@@ -341,17 +353,19 @@ int satb_dit_finalize(SatbDit* d, void* stream_v) {
   }
   if (d->adaln) SATB_REQUIRE(d->w_ssg, "adaLN to_scale_shift_gate weights missing");
   SATB_CHECK_CUDA(cudaStreamSynchronize(st));
-  std::vector<float> pin(static_cast<size_t>(D) * C), pout(static_cast<size_t>(C) * D), pre(C * C), post(C * C);
+  const int Cin = d->Cin;
+  if (d->pdim > 0) SATB_REQUIRE(d->pe0_w && d->pe2_w, "to_prepend_embed weights missing");
+  std::vector<float> pin(static_cast<size_t>(D) * Cin), pout(static_cast<size_t>(C) * D), pre(Cin * Cin), post(C * C);
   SATB_CHECK_CUDA(cudaMemcpy(pin.data(), d->pin_w, pin.size() * 4, cudaMemcpyDeviceToHost));
   SATB_CHECK_CUDA(cudaMemcpy(pout.data(), d->pout_w, pout.size() * 4, cudaMemcpyDeviceToHost));
   SATB_CHECK_CUDA(cudaMemcpy(pre.data(), d->pre_w, pre.size() * 4, cudaMemcpyDeviceToHost));
   SATB_CHECK_CUDA(cudaMemcpy(post.data(), d->post_w, post.size() * 4, cudaMemcpyDeviceToHost));
-  std::vector<float> fin(static_cast<size_t>(D) * C), fout(static_cast<size_t>(C) * D);
+  std::vector<float> fin(static_cast<size_t>(D) * Cin), fout(static_cast<size_t>(C) * D);
   for (int n = 0; n < D; ++n)
-    for (int c = 0; c < C; ++c) {
-      double acc = pin[static_cast<size_t>(n) * C + c];
-      for (int j = 0; j < C; ++j) acc += static_cast<double>(pin[static_cast<size_t>(n) * C + j]) * pre[j * C + c];
-      fin[static_cast<size_t>(n) * C + c] = static_cast<float>(acc);
+    for (int c = 0; c < Cin; ++c) {
+      double acc = pin[static_cast<size_t>(n) * Cin + c];
+      for (int j = 0; j < Cin; ++j) acc += static_cast<double>(pin[static_cast<size_t>(n) * Cin + j]) * pre[j * Cin + c];
+      fin[static_cast<size_t>(n) * Cin + c] = static_cast<float>(acc);
     }
   for (int c = 0; c < C; ++c)
     for (int k = 0; k < D; ++k) {
@@ -366,7 +380,7 @@ int satb_dit_finalize(SatbDit* d, void* stream_v) {
   SATB_CHECK_CUDA(cudaMemcpy(tmp_out, fout.data(), fout.size() * 4, cudaMemcpyHostToDevice));
   if (!d->w_in16) SATB_PROPAGATE(d->alloc(&d->w_in16, fin.size()));
   if (!d->w_out16) SATB_PROPAGATE(d->alloc(&d->w_out16, fout.size()));
-  int rc = launch_cast_rows(tmp_in, d->w_in16, nullptr, D, C, C, C, d->bf16, st);
+  int rc = launch_cast_rows(tmp_in, d->w_in16, nullptr, D, Cin, Cin, Cin, d->bf16, st);
   if (rc == 0) rc = launch_cast_rows(tmp_out, d->w_out16, nullptr, C, D, D, D, d->bf16, st);
   cudaStreamSynchronize(st);
   cudaFree(tmp_in);
@@ -442,13 +456,14 @@ int satb_dit_reserve(SatbDit* d, int R, int L) {
   SATB_PROPAGATE(d->ws_attn.ensure(M * D * 2));
   SATB_PROPAGATE(d->ws_q16.ensure(M * D * 2));
   SATB_PROPAGATE(d->ws_ff.ensure(M * d->ffi * 2));
-  SATB_PROPAGATE(d->ws_ain.ensure(M * d->C * 2));
+  SATB_PROPAGATE(d->ws_ain.ensure(M * d->Cin * 2));
   SATB_PROPAGATE(d->ws_y.ensure(M * d->C * 4));
   SATB_PROPAGATE(d->ws_stats.ensure(3 * M * kLnSlots * sizeof(float2)));
   SATB_PROPAGATE(ensure_rope(d, N_seq));
   d->tmaps.maps.clear();
   d->res_R = R;
   d->res_L = L;
+  d->res_P = d->P;
   return 0;
 }
 
@@ -470,6 +485,30 @@ static SmallWs small_ws(SatbDit* d, int R) {
 }
 
 extern "C" {
+
+// Prepend conditioning of the next prepare_cond: embeds = W2 silu(W0 prepend) (dit.py:75-81,157-161), kept as fp32
+// tokens [B, Pp, D]; the unconditional CFG rows use zeros (to_prepend_embed is bias-free, so MLP(0) = 0, dit.py:309-311).
+int satb_dit_set_prepend_cond(SatbDit* d, const float* prepend, int B, int n_tokens, void* stream_v) {
+  SATB_REQUIRE(d && d->finalized, "weights not finalized");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_v);
+  if (!prepend || n_tokens <= 0) {
+    d->Pp = 0;
+    d->P = d->adaln ? 0 : 1;
+    return 0;
+  }
+  SATB_REQUIRE(d->pdim > 0 && !d->adaln, "this model has no prepend conditioning");
+  SATB_REQUIRE(B >= 1, "bad batch");
+  const size_t rows = static_cast<size_t>(B) * n_tokens;
+  SATB_REQUIRE(rows <= 4096, "too many prepend tokens");
+  SATB_PROPAGATE(d->ws_prep.ensure(2 * rows * d->D * sizeof(float)));
+  float* emb = d->ws_prep.as<float>();
+  float* hid = emb + rows * d->D;
+  SATB_PROPAGATE(launch_skinny_linear(prepend, d->pe0_w, nullptr, nullptr, hid, static_cast<int>(rows), d->pdim, d->D, 1, st));
+  SATB_PROPAGATE(launch_skinny_linear(hid, d->pe2_w, nullptr, nullptr, emb, static_cast<int>(rows), d->D, d->D, 0, st));
+  d->Pp = n_tokens;
+  d->P = 1 + n_tokens;
+  return 0;
+}
 
 // Step-invariant conditioning work hoisted out of the sampler loop:
 // to_cond_embed, to_global_embed and every layer's cross-attention k/v projection.
@@ -585,11 +624,11 @@ static int dit_forward_impl(SatbDit* d, const float* x, const float* t, float* o
   SATB_PROPAGATE(launch_skinny_linear(sw.te_h, d->te2_w, d->te2_b, d->has_global ? sw.ge : nullptr, sw.tok, B, D, D,
                                       d->adaln ? 1 : 0, st));
   // latent -> token rows, project_in (with the 1x1 pre-conv folded), prepend token
-  SATB_PROPAGATE(launch_dit_pre(x, ain, R, B, C, L, P, BF16, st));
-  SATB_PROPAGATE((linear<EpiStore32, 256, BF16>(d->tmaps, ain, C, M, C, d->w_in16, D, EpiStore32::Params{h, D, nullptr}, st)));
+  SATB_PROPAGATE(launch_dit_pre(x, ain, R, B, d->Cin, L, P, BF16, st));
+  SATB_PROPAGATE((linear<EpiStore32, 256, BF16>(d->tmaps, ain, d->Cin, M, d->Cin, d->w_in16, D, EpiStore32::Params{h, D, nullptr}, st)));
   const int64_t ssg_ld = static_cast<int64_t>(d->depth) * 6 * D;
   if (P > 0) {
-    SATB_PROPAGATE(launch_write_prepend(sw.tok, h, R, B, N_seq, D, st));
+    SATB_PROPAGATE(launch_write_prepend(sw.tok, d->Pp > 0 ? d->ws_prep.as<float>() : nullptr, h, R, B, N_seq, D, d->Pp, st));
   } else {
     // adaLN: all layers' scale/shift/gate in one skinny GEMM (transformer.py:648-651,667)
     SATB_PROPAGATE(launch_skinny_linear(sw.tok, d->w_ssg, nullptr, nullptr, sw.ssg, B, D, d->depth * 6 * D, 0, st));
@@ -739,7 +778,7 @@ int satb_dit_forward(SatbDit* d, const float* x, const float* t, float* out, int
   SATB_REQUIRE(d && d->finalized, "weights not finalized");
   SATB_REQUIRE(B == d->B, "batch size differs from satb_dit_prepare_cond");
   const int R = d->cfg_on ? 2 * B : B;
-  if (R > d->res_R || L != d->res_L) SATB_PROPAGATE(satb_dit_reserve(d, R, L));
+  if (R > d->res_R || L != d->res_L || d->P != d->res_P) SATB_PROPAGATE(satb_dit_reserve(d, R, L));
   cudaStream_t st = static_cast<cudaStream_t>(stream_v);
   return d->bf16 ? dit_forward_impl<true>(d, x, t, out, B, L, cfg_scale, scale_phi, st, nullptr)
                  : dit_forward_impl<false>(d, x, t, out, B, L, cfg_scale, scale_phi, st, nullptr);
@@ -777,7 +816,7 @@ int satb_dit_forward_debug(SatbDit* d, const float* x, const float* t, float* ou
   SATB_REQUIRE(d && d->finalized, "weights not finalized");
   SATB_REQUIRE(B == d->B, "batch size differs from satb_dit_prepare_cond");
   const int R = d->cfg_on ? 2 * B : B;
-  if (R > d->res_R || L != d->res_L) SATB_PROPAGATE(satb_dit_reserve(d, R, L));
+  if (R > d->res_R || L != d->res_L || d->P != d->res_P) SATB_PROPAGATE(satb_dit_reserve(d, R, L));
   cudaStream_t st = static_cast<cudaStream_t>(stream_v);
   return d->bf16 ? dit_forward_impl<true>(d, x, t, out, B, L, cfg_scale, scale_phi, st, hidden)
                  : dit_forward_impl<false>(d, x, t, out, B, L, cfg_scale, scale_phi, st, hidden);

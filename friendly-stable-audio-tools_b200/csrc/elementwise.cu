@@ -262,10 +262,17 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restr
   }
 }
 
-__global__ void write_prepend_kernel(const float* __restrict__ tok, float* __restrict__ h, int B, int N_seq, int D) {
-  const int r = blockIdx.y;
+// rows 0 .. Pp-1 of every item: the prepend-conditioning tokens (conditional rows r < B; zeros for the unconditional CFG
+// rows, dit.py:309-311); row Pp: the global-conditioning token (dit.py:185-195)
+__global__ void write_prepend_kernel(const float* __restrict__ tok, const float* __restrict__ pre, float* __restrict__ h, int B,
+                                     int N_seq, int D, int Pp) {
+  const int r = blockIdx.y, j = blockIdx.z;
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d < D) h[static_cast<size_t>(r) * N_seq * D + d] = tok[static_cast<size_t>(r % B) * D + d];
+  if (d >= D) return;
+  float v;
+  if (j < Pp) v = (r < B && pre) ? pre[(static_cast<size_t>(r) * Pp + j) * D + d] : 0.f;
+  else v = tok[static_cast<size_t>(r % B) * D + d];
+  h[(static_cast<size_t>(r) * N_seq + j) * D + d] = v;
 }
 
 __global__ void gate_sigmoid_kernel(float* __restrict__ ssg, int depth, int D) {
@@ -506,9 +513,10 @@ int launch_skinny_linear(const float* in, const float* W, const float* bias, con
   return 0;
 }
 
-int launch_write_prepend(const float* tok, float* h, int R, int B, int N_seq, int D, cudaStream_t stream) {
-  dim3 grid(ceil_div(D, 256), R);
-  write_prepend_kernel<<<grid, 256, 0, stream>>>(tok, h, B, N_seq, D);
+int launch_write_prepend(const float* tok, const float* pre, float* h, int R, int B, int N_seq, int D, int Pp,
+                         cudaStream_t stream) {
+  dim3 grid(ceil_div(D, 256), R, Pp + 1);
+  write_prepend_kernel<<<grid, 256, 0, stream>>>(tok, pre, h, B, N_seq, D, Pp);
   count_launch();
   SATB_CHECK_CUDA(cudaGetLastError());
   return 0;

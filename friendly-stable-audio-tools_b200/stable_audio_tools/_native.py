@@ -23,7 +23,8 @@ class NativeError(RuntimeError):
 class SatbDitConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in (
         "io_channels", "embed_dim", "depth", "num_heads", "cond_token_dim", "global_cond_dim",
-        "project_cond_tokens", "project_global_cond", "global_cond_type", "patch_size", "operand_dtype", "qk_norm")]
+        "project_cond_tokens", "project_global_cond", "global_cond_type", "patch_size", "operand_dtype", "qk_norm",
+        "input_concat_dim", "prepend_cond_dim")]
 
 
 SATB_MAX_STAGES = 8
@@ -49,6 +50,7 @@ SIGNATURES = {
     "satb_dit_load_weight": (_I, [_VP, ctypes.c_char_p, _VP, _LL, _VP]),
     "satb_dit_finalize": (_I, [_VP, _VP]),
     "satb_dit_reserve": (_I, [_VP, _I, _I]),
+    "satb_dit_set_prepend_cond": (_I, [_VP, _VP, _I, _I, _VP]),
     "satb_dit_prepare_cond": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "satb_dit_forward": (_I, [_VP, _VP, _VP, _VP, _I, _I, _F, _F, _VP]),
     "satb_dit_forward_debug": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _F, _F, _VP]),

@@ -46,8 +46,8 @@ class DiffusionTransformer(nn.Module):
         if transformer_type != "continuous_transformer":
             raise NotImplementedError("only transformer_type='continuous_transformer' is on the native hot path "
                                       "(the reference's x-transformers branch needs an un-vendored dependency)")
-        if input_concat_dim != 0 or prepend_cond_dim != 0:
-            raise NotImplementedError("input_concat / prepend_cond are not on the native hot path yet")
+        if prepend_cond_dim > 0 and global_cond_type != "prepend":
+            raise NotImplementedError("prepend_cond with global_cond_type='adaLN' is not on the native hot path")
         if patch_size < 1:
             raise ValueError("patch_size must be >= 1")
         if global_cond_type not in ("prepend", "adaLN"):
@@ -55,6 +55,7 @@ class DiffusionTransformer(nn.Module):
         self.patch_size = patch_size
         self.cond_token_dim = cond_token_dim
         self.input_concat_dim = input_concat_dim
+        self.prepend_cond_dim = prepend_cond_dim
         self.io_channels = io_channels
         self.embed_dim = embed_dim
         self.depth = depth
@@ -80,11 +81,15 @@ class DiffusionTransformer(nn.Module):
             glob_embed_dim = embed_dim if project_global_cond else global_cond_dim
             self.to_global_embed = nn.Sequential(nn.Linear(global_cond_dim, glob_embed_dim, bias=False), nn.SiLU(),
                                                  nn.Linear(glob_embed_dim, glob_embed_dim, bias=False))
+        if prepend_cond_dim > 0:                                   # dit.py:75-81
+            self.to_prepend_embed = nn.Sequential(nn.Linear(prepend_cond_dim, embed_dim, bias=False), nn.SiLU(),
+                                                  nn.Linear(embed_dim, embed_dim, bias=False))
+        dim_in = io_channels + input_concat_dim                    # dit.py:38
         self.transformer = ContinuousTransformer(
-            dim=embed_dim, depth=depth, dim_heads=embed_dim // num_heads, dim_in=io_channels * patch_size,
+            dim=embed_dim, depth=depth, dim_heads=embed_dim // num_heads, dim_in=dim_in * patch_size,
             dim_out=io_channels * patch_size, cross_attend=cond_token_dim > 0, cond_token_dim=cond_embed_dim,
             global_cond_dim=embed_dim if global_cond_type == "adaLN" else None, **kwargs)
-        self.preprocess_conv = nn.Conv1d(io_channels, io_channels, 1, bias=False)
+        self.preprocess_conv = nn.Conv1d(dim_in, dim_in, 1, bias=False)
         nn.init.zeros_(self.preprocess_conv.weight)
         self.postprocess_conv = nn.Conv1d(io_channels, io_channels, 1, bias=False)
         nn.init.zeros_(self.postprocess_conv.weight)
@@ -135,7 +140,8 @@ class DiffusionTransformer(nn.Module):
                 cond_token_dim=self.cond_token_dim, global_cond_dim=self.global_cond_dim,
                 project_cond_tokens=int(self.project_cond_tokens), project_global_cond=int(self.project_global_cond),
                 global_cond_type=1 if self.global_cond_type == "adaLN" else 0, patch_size=1,
-                operand_dtype=1 if self.operand_dtype == "bf16" else 0, qk_norm=int(self.qk_norm))
+                operand_dtype=1 if self.operand_dtype == "bf16" else 0, qk_norm=int(self.qk_norm),
+                input_concat_dim=self.input_concat_dim * self.patch_size, prepend_cond_dim=self.prepend_cond_dim)
             h = ctypes.c_void_p()
             _native.check(lib.satb_dit_create(ctypes.byref(cfg), ctypes.byref(h)))
             self.__dict__["_h"] = h
@@ -165,20 +171,25 @@ class DiffusionTransformer(nn.Module):
     def _tkey(t):
         return None if t is None else (t.data_ptr(), t._version, tuple(t.shape), str(t.dtype))
 
-    def _prepare(self, h, cross, neg, glob, use_cfg, device, B):
-        key = (self._tkey(cross), self._tkey(neg), self._tkey(glob), bool(use_cfg), B)
+    def _prepare(self, h, cross, neg, glob, use_cfg, device, B, prepend=None):
+        key = (self._tkey(cross), self._tkey(neg), self._tkey(glob), bool(use_cfg), B, self._tkey(prepend))
         if key == self.__dict__["_cond_key"]:
             return
         f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
-        c, n, g = f32(cross), f32(neg), f32(glob)
-        for name, tt in (("cross_attn_cond", c), ("negative_cross_attn_cond", n), ("global_embed", g)):
+        c, n, g, pc = f32(cross), f32(neg), f32(glob), f32(prepend)
+        for name, tt in (("cross_attn_cond", c), ("negative_cross_attn_cond", n), ("global_embed", g),
+                         ("prepend_cond", pc)):
             if tt is not None and tt.shape[0] != B:
                 raise ValueError(f"{name} batch {tt.shape[0]} != input batch {B}")
         Mctx = c.shape[1] if c is not None else 0
+        if pc is not None and pc.shape[2] != self.prepend_cond_dim:
+            raise ValueError(f"prepend_cond width {pc.shape[2]} != prepend_cond_dim {self.prepend_cond_dim}")
+        _native.check(_native.lib().satb_dit_set_prepend_cond(h, _native.ptr(pc), B, pc.shape[1] if pc is not None else 0,
+                                                              _native.stream_ptr(device)))
         _native.check(_native.lib().satb_dit_prepare_cond(h, _native.ptr(c), _native.ptr(n), _native.ptr(g), B, Mctx,
                                                           1 if use_cfg else 0, _native.stream_ptr(device)))
         self.__dict__["_cond_key"] = key
-        self.__dict__["_keepalive"] = (cross, neg, glob)   # keep the keyed storage alive
+        self.__dict__["_keepalive"] = (cross, neg, glob, prepend)   # keep the keyed storage alive
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
@@ -188,8 +199,11 @@ class DiffusionTransformer(nn.Module):
                 return_info=False, **kwargs):
         if causal:
             raise AssertionError("Causal mode is not supported for DiffusionTransformer")
-        if input_concat_cond is not None or prepend_cond is not None:
-            raise NotImplementedError("input_concat_cond / prepend_cond are not on the native hot path yet")
+        if prepend_cond is not None and self.prepend_cond_dim == 0:
+            raise ValueError("prepend_cond given to a model built with prepend_cond_dim=0")
+        if (input_concat_cond is None) != (self.input_concat_dim == 0):
+            raise ValueError("input_concat_cond must be given exactly when the model has input_concat_dim > 0 "
+                             f"(input_concat_dim={self.input_concat_dim})")
         if self.training and cfg_dropout_prob > 0.0:
             raise NotImplementedError("training-time CFG dropout is outside the inference hot path")
         if not x.is_cuda:
@@ -198,7 +212,14 @@ class DiffusionTransformer(nn.Module):
         # transformer.py:787-802 never forwards them to the layers)
         if cross_attn_cond is not None and self.cond_token_dim == 0:
             cross_attn_cond = None
-        use_cfg = cfg_scale != 1.0 and cross_attn_cond is not None
+        use_cfg = cfg_scale != 1.0 and (cross_attn_cond is not None or prepend_cond is not None)   # dit.py:270
+        if input_concat_cond is not None:
+            # dit.py:163-168: nearest-neighbour resize to the latent length, channel concat in front of the 1x1
+            # pre-conv (which the native finalize folds into project_in over all io + concat channels); the CFG
+            # halves share it (dit.py:281-284), as they share x
+            if input_concat_cond.shape[2] != x.shape[2]:
+                input_concat_cond = torch.nn.functional.interpolate(input_concat_cond, (x.shape[2],), mode="nearest")
+            x = torch.cat([x, input_concat_cond.to(x.dtype)], dim=1)
         neg = None
         if use_cfg and negative_cross_attn_cond is not None:
             neg = negative_cross_attn_cond
@@ -224,7 +245,11 @@ class DiffusionTransformer(nn.Module):
                 # conditional outputs from two native calls and rescale here (device tensors, torch elementwise)
                 kw = dict(cross_attn_cond=cross_attn_cond, cross_attn_cond_mask=cross_attn_cond_mask,
                           negative_cross_attn_cond=negative_cross_attn_cond,
-                          negative_cross_attn_mask=negative_cross_attn_mask, global_embed=global_embed)
+                          negative_cross_attn_mask=negative_cross_attn_mask, global_embed=global_embed,
+                          prepend_cond=prepend_cond)
+                if input_concat_cond is not None:                  # x already carries it: split it off again
+                    kw["input_concat_cond"] = x[:, self.io_channels:]
+                    x = x[:, :self.io_channels]
                 cfg_out = self.forward(x, t, cfg_scale=cfg_scale, scale_phi=0.0, **kw)
                 cond_out = self.forward(x, t, cfg_scale=1.0, scale_phi=0.0, **kw)
                 rescaled = cfg_out * (cond_out.std(dim=1, keepdim=True) / cfg_out.std(dim=1, keepdim=True))
@@ -237,13 +262,13 @@ class DiffusionTransformer(nn.Module):
         with torch.cuda.device(x.device):
             h = self._handle(x.device)
             B, C, L = x.shape
-            self._prepare(h, cross_attn_cond, neg, global_embed, use_cfg, x.device, B)
+            self._prepare(h, cross_attn_cond, neg, global_embed, use_cfg, x.device, B, prepend_cond)
             xin = x.detach().to(torch.float32).contiguous()
             tin = t.detach().to(torch.float32).contiguous()
-            out = torch.empty_like(xin)
+            out = torch.empty(B, self.io_channels * p, L, device=x.device, dtype=torch.float32)
             st = _native.stream_ptr(x.device)
             if return_info:
-                P = 0 if self.global_cond_type == "adaLN" else 1
+                P = 0 if self.global_cond_type == "adaLN" else 1 + (prepend_cond.shape[1] if prepend_cond is not None else 0)
                 rows = (2 * B if use_cfg else B) * (L + P)
                 hidden = torch.empty(rows, self.embed_dim, device=x.device, dtype=torch.float32)
                 _native.check(_native.lib().satb_dit_forward_debug(h, _native.ptr(xin), _native.ptr(tin), _native.ptr(out),
@@ -268,7 +293,8 @@ class DiffusionTransformer(nn.Module):
         key = (B, L, cfg_scale, scale_phi, self.__dict__["_cond_key"], device.index)
         g = self.__dict__["_graph"]
         if g is None or g["key"] != key:
-            sx, st_, so = torch.empty_like(xin), torch.empty_like(tin), torch.empty_like(xin)
+            sx, st_ = torch.empty_like(xin), torch.empty_like(tin)
+            so = torch.empty(B, self.io_channels * self.patch_size, L, device=xin.device, dtype=torch.float32)
             sx.copy_(xin)
             st_.copy_(tin)
 

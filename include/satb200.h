@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define SATB_ABI_VERSION 2
+#define SATB_ABI_VERSION 3
 
 typedef struct SatbDit SatbDit;
 typedef struct SatbOobleck SatbOobleck;
@@ -41,6 +41,9 @@ typedef struct SatbDitConfig {
   int operand_dtype;        /* 0 = fp16 (the reference's autocast dtype), 1 = bf16 */
   int qk_norm;              /* 1 = L2-normalise q and k per head before RoPE / attention
                                (attn_kwargs.qk_norm, models/transformer.py:298,433-436) */
+  int input_concat_dim;     /* extra input channels concatenated to x before the 1x1 pre-conv (dit.py:38,163-168); the
+                               caller passes x with io_channels + input_concat_dim channels */
+  int prepend_cond_dim;     /* width of the prepend conditioning tokens (dit.py:75-81), 0 = none */
 } SatbDitConfig;
 
 /* Mirrors OobleckEncoder/OobleckDecoder kwargs (models/autoencoders.py:119-194). */
@@ -81,6 +84,10 @@ int satb_dit_reserve(SatbDit* h, int rows, int L);
 /* Step-invariant conditioning (dit.py:149-154 to_cond_embed / to_global_embed, and every
  * layer's cross-attention to_kv, transformer.py:425): cross [B, Mctx, cond_token_dim],
  * neg_cross (same shape, or NULL), global [B, global_cond_dim] (or NULL); device fp32. */
+/* Prepend conditioning for the NEXT satb_dit_prepare_cond (dit.py:157-161,185-195,309-311): prepend [B, n_tokens,
+ * prepend_cond_dim] device fp32 (NULL / 0 tokens = none).  Its to_prepend_embed tokens go in front of the
+ * global-conditioning token; the unconditional CFG rows get zeros.  "prepend" global_cond_type only. */
+int satb_dit_set_prepend_cond(SatbDit* h, const float* prepend, int B, int n_tokens, void* stream);
 int satb_dit_prepare_cond(SatbDit* h, const float* cross, const float* neg_cross, const float* global, int B,
                           int Mctx, int use_cfg, void* stream);
 /* One denoiser call = DiffusionTransformer.forward (dit.py:228-364): x [B, C, L], t [B] ->

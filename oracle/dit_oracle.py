@@ -208,9 +208,12 @@ def _mlp(x, sd, name):
     return _lin(F.silu(_lin(x, sd[name + ".0.weight"], b0)), sd[name + ".2.weight"], b2)
 
 
-def dit_inner_forward(sd, cfg, x, t, cross_attn_cond=None, global_embed=None, hidden_states=None):
-    """models/dit.py:135-226 (``_forward``), continuous_transformer backbone,
-    optional patching (dit.py:206-207,221-222), no input_concat / prepend_cond."""
+def dit_inner_forward(sd, cfg, x, t, cross_attn_cond=None, global_embed=None, hidden_states=None,
+                      input_concat_cond=None, prepend_cond=None):
+    """models/dit.py:135-226 (``_forward``), continuous_transformer backbone, optional patching
+    (dit.py:206-207,221-222), input_concat_cond (:163-168: nearest-neighbour resize to the latent length, channel
+    concat before the 1x1 pre-conv) and prepend_cond (:157-161,185-195: to_prepend_embed MLP, its tokens in front of
+    the global-conditioning token; "prepend" mode only)."""
     patch = cfg.get("patch_size", 1)
     depth = cfg["depth"]
     dim_heads = cfg["embed_dim"] // cfg["num_heads"]
@@ -224,9 +227,16 @@ def dit_inner_forward(sd, cfg, x, t, cross_attn_cond=None, global_embed=None, hi
     global_embed = te if global_embed is None else global_embed + te             # dit.py:179-182
     prepend = None
     prepend_length = 0
+    if prepend_cond is not None:
+        prepend = _mlp(prepend_cond, sd, "to_prepend_embed")                     # dit.py:157-161 (bias-free MLP)
+    if input_concat_cond is not None:                                            # dit.py:163-168
+        if input_concat_cond.shape[2] != x.shape[2]:
+            input_concat_cond = F.interpolate(input_concat_cond, (x.shape[2],), mode="nearest")
+        x = torch.cat([x, input_concat_cond], dim=1)
     if gtype == "prepend":
-        prepend = global_embed.unsqueeze(1)                                      # dit.py:185-195
-        prepend_length = 1
+        tok = global_embed.unsqueeze(1)                                          # dit.py:185-195
+        prepend = tok if prepend is None else torch.cat([prepend, tok], dim=1)
+        prepend_length = prepend.shape[1]
     x = F.conv1d(x, sd["preprocess_conv.weight"]) + x                            # dit.py:197
     x = x.transpose(1, 2)
     if patch > 1:                                                                # "b (t p) c -> b t (c p)"
@@ -245,23 +255,27 @@ def dit_inner_forward(sd, cfg, x, t, cross_attn_cond=None, global_embed=None, hi
 
 def dit_forward(sd, cfg, x, t, cross_attn_cond=None, global_embed=None,
                 negative_cross_attn_cond=None, negative_cross_attn_mask=None,
-                cfg_scale=1.0, scale_phi=0.0):
+                cfg_scale=1.0, scale_phi=0.0, input_concat_cond=None, prepend_cond=None):
     """models/dit.py:228-364 (``forward``), eval mode: batched CFG (cond rows
     first, uncond rows second; null cond = zeros, or the negative cond),
     ``uncond + (cond - uncond) * cfg_scale`` and the optional std rescale."""
-    if cfg_scale != 1.0 and cross_attn_cond is not None:
-        null = torch.zeros_like(cross_attn_cond)
-        if negative_cross_attn_cond is not None:
-            neg = negative_cross_attn_cond
-            if negative_cross_attn_mask is not None:
-                neg = torch.where(negative_cross_attn_mask.to(torch.bool).unsqueeze(2), neg, null)
-            batch_cond = torch.cat([cross_attn_cond, neg], dim=0)
-        else:
-            batch_cond = torch.cat([cross_attn_cond, null], dim=0)
+    if cfg_scale != 1.0 and (cross_attn_cond is not None or prepend_cond is not None):   # dit.py:270
+        batch_cond = None
+        if cross_attn_cond is not None:
+            null = torch.zeros_like(cross_attn_cond)
+            if negative_cross_attn_cond is not None:
+                neg = negative_cross_attn_cond
+                if negative_cross_attn_mask is not None:
+                    neg = torch.where(negative_cross_attn_mask.to(torch.bool).unsqueeze(2), neg, null)
+                batch_cond = torch.cat([cross_attn_cond, neg], dim=0)
+            else:
+                batch_cond = torch.cat([cross_attn_cond, null], dim=0)
         bx = torch.cat([x, x], dim=0)
         bt = torch.cat([t, t], dim=0)
         bg = None if global_embed is None else torch.cat([global_embed, global_embed], dim=0)
-        out = dit_inner_forward(sd, cfg, bx, bt, batch_cond, bg)
+        bic = None if input_concat_cond is None else torch.cat([input_concat_cond, input_concat_cond], dim=0)   # :281-284
+        bpc = None if prepend_cond is None else torch.cat([prepend_cond, torch.zeros_like(prepend_cond)], dim=0)  # :309-311
+        out = dit_inner_forward(sd, cfg, bx, bt, batch_cond, bg, input_concat_cond=bic, prepend_cond=bpc)
         cond_out, uncond_out = torch.chunk(out, 2, dim=0)
         cfg_out = uncond_out + (cond_out - uncond_out) * cfg_scale
         if scale_phi != 0.0:
@@ -269,7 +283,8 @@ def dit_forward(sd, cfg, x, t, cross_attn_cond=None, global_embed=None,
             cfg_std = cfg_out.std(dim=1, keepdim=True)
             return scale_phi * (cfg_out * (cond_std / cfg_std)) + (1 - scale_phi) * cfg_out
         return cfg_out
-    return dit_inner_forward(sd, cfg, x, t, cross_attn_cond, global_embed)
+    return dit_inner_forward(sd, cfg, x, t, cross_attn_cond, global_embed, input_concat_cond=input_concat_cond,
+                             prepend_cond=prepend_cond)
 
 
 # ---------------------------------------------------------------------------
@@ -282,7 +297,8 @@ def dit_param_shapes(cfg):
     reference state-dict layout."""
     D = cfg["embed_dim"]
     io = cfg["io_channels"]
-    iop = io * cfg.get("patch_size", 1)
+    cin = io + cfg.get("input_concat_dim", 0)                                    # dit.py:38
+    iop, cinp = io * cfg.get("patch_size", 1), cin * cfg.get("patch_size", 1)
     ct = cfg.get("cond_token_dim", 0)
     gd = cfg.get("global_cond_dim", 0)
     cond_embed = D if cfg.get("project_cond_tokens", True) else ct
@@ -292,8 +308,8 @@ def dit_param_shapes(cfg):
         "timestep_features.weight": (128, 1),
         "to_timestep_embed.0.weight": (D, 256), "to_timestep_embed.0.bias": (D,),
         "to_timestep_embed.2.weight": (D, D), "to_timestep_embed.2.bias": (D,),
-        "preprocess_conv.weight": (io, io, 1), "postprocess_conv.weight": (io, io, 1),
-        "transformer.project_in.weight": (D, iop), "transformer.project_out.weight": (iop, D),
+        "preprocess_conv.weight": (cin, cin, 1), "postprocess_conv.weight": (io, io, 1),
+        "transformer.project_in.weight": (D, cinp), "transformer.project_out.weight": (iop, D),
         "transformer.rotary_pos_emb.inv_freq": (max(dh // 2, 32) // 2,),
     }
     if ct > 0:
@@ -302,6 +318,9 @@ def dit_param_shapes(cfg):
     if gd > 0:
         shapes["to_global_embed.0.weight"] = (glob_embed, gd)
         shapes["to_global_embed.2.weight"] = (glob_embed, glob_embed)
+    if cfg.get("prepend_cond_dim", 0) > 0:
+        shapes["to_prepend_embed.0.weight"] = (D, cfg["prepend_cond_dim"])
+        shapes["to_prepend_embed.2.weight"] = (D, D)
     adaln = cfg.get("global_cond_type", "prepend") == "adaLN"
     for i in range(cfg["depth"]):
         p = f"transformer.layers.{i}."

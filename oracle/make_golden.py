@@ -72,6 +72,34 @@ def gen_dit(ref, gtype, path, patch_size=1, qk_norm=False):
     np.savez_compressed(path, **out)
 
 
+def gen_dit_concat_prepend(ref, path):
+    """input_concat_cond (16 extra channels, half the latent length: exercises the nearest-neighbour resize) and
+    prepend_cond (3 tokens of width 96) through the real DiffusionTransformer (models/dit.py:157-173,185-195,281-311)."""
+    cfg = dict(DIT_SMALL, input_concat_dim=16, prepend_cond_dim=96)
+    seed = 15
+    sd = do.make_dit_weights(cfg, seed=seed)
+    m = ref.dit.DiffusionTransformer(**cfg).eval()
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(100 + seed)
+    B, L, M = 2, 200, 10
+    x = torch.randn(B, 64, L, generator=g)
+    t = torch.rand(B, generator=g)
+    c = torch.randn(B, M, 128, generator=g)
+    ge = torch.randn(B, 256, generator=g)
+    ic = torch.randn(B, 16, L // 2, generator=g)
+    pc = torch.randn(B, 3, 96, generator=g)
+    out = {"cfg": json.dumps(cfg), "seed": seed, "wsum": weights_checksum(sd),
+           "x": _np(x), "t": _np(t), "cross": _np(c), "glob": _np(ge), "concat": _np(ic), "prepend": _np(pc)}
+    kw = dict(cross_attn_cond=c, global_embed=ge, input_concat_cond=ic, prepend_cond=pc,
+              prepend_cond_mask=torch.ones(B, 3, dtype=torch.bool))
+    with torch.no_grad():
+        out["y_nocfg"] = _np(m(x, t, cfg_scale=1.0, **kw))
+        out["y_cfg5"] = _np(m(x, t, cfg_scale=5.0, **kw))
+        out["y_cfg3_phi"] = _np(m(x, t, cfg_scale=3.0, scale_phi=0.5, **kw))
+        out["y_concat_only"] = _np(m(x, t, cross_attn_cond=c, global_embed=ge, input_concat_cond=ic, cfg_scale=4.0))
+    np.savez_compressed(path, **out)
+
+
 def gen_rope(ref, path):
     rot = ref.transformer.RotaryEmbedding(32)
     freqs, _ = rot.forward_from_seq_len(1025)
@@ -202,6 +230,7 @@ def main():
     gen_dit(ref, "adaLN", os.path.join(GOLDEN_DIR, "dit_adaln_small.npz"))
     gen_dit(ref, "prepend", os.path.join(GOLDEN_DIR, "dit_patch2_small.npz"), patch_size=2)
     gen_dit(ref, "prepend", os.path.join(GOLDEN_DIR, "dit_qknorm_small.npz"), qk_norm=True)
+    gen_dit_concat_prepend(ref, os.path.join(GOLDEN_DIR, "dit_concat_prepend_small.npz"))
     gen_rope(ref, os.path.join(GOLDEN_DIR, "rope_1025.npz"))
     gen_snake(ref, os.path.join(GOLDEN_DIR, "snake_beta.npz"))
     gen_oobleck(ref, os.path.join(GOLDEN_DIR, "oobleck_small.npz"))

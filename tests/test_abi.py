@@ -28,7 +28,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for s in _header_symbols():
         assert hasattr(lib, s), f"{s} declared in include/satb200.h but not exported"
     assert set(_native.SIGNATURES) == set(_header_symbols()), "ctypes signature table out of sync with the header"
-    assert lib.satb_abi_version() == 2
+    assert lib.satb_abi_version() == 3
 
 
 def test_create_validates_config_and_reports_errors():

@@ -57,6 +57,61 @@ def test_dit_small_vs_reference_golden(name, dtype):
     assert err < TOL[dtype], f"{name} hidden {dtype}: rel l2 {err}"
 
 
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+def test_dit_input_concat_and_prepend_cond_vs_reference_golden(dtype):
+    """input_concat_cond (half-length: nearest-neighbour resize; 16 extra channels folded through the 1x1 pre-conv into
+    project_in) and prepend_cond (3 to_prepend_embed tokens in front of the global token, zeros on the unconditional
+    CFG rows) against the real DiffusionTransformer (dit.py:157-173,185-195,281-311)."""
+    g, cfg, sd = _golden_case("dit_concat_prepend_small.npz")
+    m = build_native_dit(cfg, sd, operand_dtype=dtype)
+    T = lambda k: torch.from_numpy(g[k]).cuda()
+    x, t = T("x"), T("t")
+    kw = dict(cross_attn_cond=T("cross"), global_embed=T("glob"), input_concat_cond=T("concat"))
+    full = dict(kw, prepend_cond=T("prepend"), prepend_cond_mask=torch.ones(2, 3, dtype=torch.bool, device="cuda"))
+    cases = [("y_nocfg", full, dict(cfg_scale=1.0)), ("y_cfg5", full, dict(cfg_scale=5.0)),
+             ("y_cfg3_phi", full, dict(cfg_scale=3.0, scale_phi=0.5)), ("y_concat_only", kw, dict(cfg_scale=4.0)),
+             ("y_cfg5", full, dict(cfg_scale=5.0))]          # again after a no-prepend call: P 4 -> 1 -> 4 re-reserves
+    for key, cond, extra in cases:
+        y = m(x, t, **cond, **extra)
+        assert y.shape == x.shape
+        err = rel_l2(y.cpu(), torch.from_numpy(g[key]))
+        assert err < tol(dtype, extra["cfg_scale"]), f"{key} {dtype}: rel l2 {err}"
+    y, info = m(x, t, cfg_scale=1.0, return_info=True, **full)
+    assert info["hidden_states"][-1].shape == (2, 200 + 4, 256)
+    m.cuda_graph = True                                       # the captured forward carries the prepend tokens too
+    y1 = m(x, t, cfg_scale=5.0, **full)
+    assert rel_l2(y1.cpu(), torch.from_numpy(g["y_cfg5"])) < tol(dtype, 5.0)
+    with pytest.raises(ValueError):
+        m(x, t, cross_attn_cond=T("cross"), global_embed=T("glob"))          # the model needs its concat input
+
+
+def test_dit_prepend_cond_only_guidance_and_patched_concat_vs_oracle():
+    """(a) CFG is on when only prepend_cond is given (dit.py:270): no cross-attention rows at all; (b) patch_size 2
+    together with input_concat_cond: the concat channels are patched with x ("b c (t p) -> b (c p) t" over all
+    io + concat channels, dit.py:206-207) and only io_channels come back."""
+    from oracle import dit_oracle as do
+    base = dict(io_channels=64, embed_dim=256, depth=2, num_heads=4, cond_token_dim=0, global_cond_dim=256,
+                transformer_type="continuous_transformer")
+    g = torch.Generator().manual_seed(3)
+    x, t = torch.randn(2, 64, 96, generator=g), torch.rand(2, generator=g)
+    ge, pc = torch.randn(2, 256, generator=g), torch.randn(2, 5, 32, generator=g)
+    cfg = dict(base, prepend_cond_dim=32)
+    sd = do.make_dit_weights(cfg, seed=21)
+    m = build_native_dit(cfg, sd)
+    ref = do.dit_forward(sd, cfg, x, t, global_embed=ge, prepend_cond=pc, cfg_scale=3.0)
+    y = m(x.cuda(), t.cuda(), global_embed=ge.cuda(), prepend_cond=pc.cuda(), cfg_scale=3.0).cpu()
+    assert rel_l2(y, ref) < tol("fp16", 3.0)
+    cfg = dict(base, cond_token_dim=128, project_cond_tokens=False, input_concat_dim=8, patch_size=2)
+    sd = do.make_dit_weights(cfg, seed=22)
+    m = build_native_dit(cfg, sd)
+    c, ic = torch.randn(2, 7, 128, generator=g), torch.randn(2, 8, 96, generator=g)
+    for kw in (dict(cfg_scale=1.0), dict(cfg_scale=4.0), dict(cfg_scale=4.0, scale_phi=0.6)):
+        ref = do.dit_forward(sd, cfg, x, t, cross_attn_cond=c, global_embed=ge, input_concat_cond=ic, **kw)
+        y = m(x.cuda(), t.cuda(), cross_attn_cond=c.cuda(), global_embed=ge.cuda(), input_concat_cond=ic.cuda(), **kw).cpu()
+        assert y.shape == x.shape
+        assert rel_l2(y, ref) < tol("fp16", kw["cfg_scale"]), kw
+
+
 def test_dit_repeat_call_is_deterministic_and_cache_safe():
     g, cfg, sd = _golden_case("dit_prepend_small.npz")
     m = build_native_dit(cfg, sd)

@@ -253,10 +253,14 @@ def test_unsupported_dit_inputs_fail_loudly_on_the_host():
                 project_cond_tokens=False)
     with pytest.raises(NotImplementedError):
         DiffusionTransformer(**base, transformer_type="x-transformers")
-    with pytest.raises(NotImplementedError):
-        DiffusionTransformer(**base, transformer_type="continuous_transformer", input_concat_dim=8)
-    with pytest.raises(NotImplementedError):
-        DiffusionTransformer(**base, transformer_type="continuous_transformer", prepend_cond_dim=8)
+    with pytest.raises(NotImplementedError):                             # prepend tokens need the "prepend" layout
+        DiffusionTransformer(**base, transformer_type="continuous_transformer", prepend_cond_dim=8,
+                             global_cond_type="adaLN")
+    mc = DiffusionTransformer(**base, transformer_type="continuous_transformer", input_concat_dim=8, prepend_cond_dim=32)
+    assert mc.preprocess_conv.weight.shape == (72, 72, 1) and mc.transformer.project_in.weight.shape == (256, 72)
+    assert mc.to_prepend_embed[0].weight.shape == (256, 32) and mc.postprocess_conv.weight.shape == (64, 64, 1)
+    with pytest.raises(ValueError):                                      # concat input missing
+        mc(torch.randn(1, 64, 32), torch.rand(1))
     m = DiffusionTransformer(**base, transformer_type="continuous_transformer", patch_size=2,
                              attn_kwargs={"qk_norm": True})
     assert m.patch_size == 2 and m.qk_norm and m.transformer.layers[0].self_attn.qk_norm
