@@ -519,7 +519,7 @@ def run_native(args):
                             "frac_of_hbm_peak_survey_denominator": survey_gb / (dec_ms_sample / 1e3) / hbm_peak,
                             "roofline_floor_ms": max(dec_flops / (peak_tf * 1e12), dec_bytes / (hbm_peak * 1e9)) * 1e3,
                             "byte_model": "profiles/tools/decoder_bytes.py",
-                            # operand_dtype="fp16x3": 3 MMAs per product, fp32 skip stream, ~60 dB instead of ~40 dB vs fp32
+                            # operand_dtype="fp16x3": 3 MMAs per product, fp32 skip stream, ~73 dB instead of ~40 dB vs fp32
                             "fp16x3_ms_per_sample": dec_x3_ms,
                             "audio_sec_per_s_100step_fp16x3": (world * BATCH * AUDIO_SECONDS /
                                                                ((GEN_STEPS * ms_per_step + BATCH * dec_x3_ms) / 1e3))

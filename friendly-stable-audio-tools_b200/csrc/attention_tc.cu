@@ -51,10 +51,15 @@ constexpr int kRowPathMax = 2;                               // Nq % 128 <= this
 constexpr int kAttnThreads = 384;                            // 4 control warps + 8 softmax warps
 constexpr int kSoftmaxThreads = 256;
 constexpr int kAttnPolyDefault = 0;                          // see SATB_ATTN_POLY
+constexpr int kAttnSlotsDefault = 2;                         // see SATB_ATTN_SLOTS
 constexpr int kExtraMax = 2;                                 // Nk % 128 <= this: those keys are added in the epilogue
 constexpr int kXRows = 16;                                   // rows of the leftover-key K / V tiles (TMA box)
 constexpr int kXBytes = kXRows * kD * 2;                     // 2 KB
-constexpr int kAttnSmem = kQBytes + 2 * kStagesKV * kKVBytes + 4 * kXBytes + kRowChunk * 4 + 4 * 2 * kQ * 4 + 256 + 1024;   // 97.25 KB
+// shared memory of one pipeline ("slot"): Q, K / V rings, leftover-key boxes, row-path scratch, exchange slots, barriers
+constexpr int kSlotSmem = (kQBytes + 2 * kStagesKV * kKVBytes + 4 * kXBytes + kRowChunk * 4 + 4 * 2 * kQ * 4 + 256 + 1023) & ~1023;   // 97 KB
+constexpr int attn_smem_bytes(int slots) { return slots * kSlotSmem + 1024; }
+constexpr int kWarpsPerSlot = kAttnThreads / 32;
+constexpr int kAltSpinMax = 400;                             // safety valve of the turn-taking below (never a correctness matter)
 constexpr int kTmemColsAttn = 256;
 constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;
 constexpr float kRescaleThreshold = 8.0f;                    // log2 units
@@ -71,6 +76,7 @@ struct AttnTcArgs {
   const uint16_t *q, *k, *v; // raw pointers for the row path
   int64_t ldq, ldk, ldv, q_bs, k_bs, v_bs;
   float scale_log2;
+  int alternate;             // SLOTS == 2: the two pipelines of a CTA take turns on the SFU (see attn_tc_kernel)
   unsigned long long* dbg;   // optional clock64 trace of CTA 0's first softmax warp (tests / profiles only)
 };
 
@@ -277,13 +283,27 @@ __device__ void attn_row_path(const AttnTcArgs& p, int b, int h, int row, float*
 }
 
 // POLY: every fourth pair of exponentials of a full chunk goes through ex2_poly2 (FMA / ALU pipes) instead of the SFU
-template <bool BF16, bool POLY>
-__global__ void __launch_bounds__(kAttnThreads, 2)
+// SLOTS: pipelines per CTA.  1: a CTA of 384 threads is one pipeline, two CTAs share an SM.  2: ONE CTA of 768 threads
+// per SM runs two complete pipelines (warps 0-11 and 12-23, each with its own shared-memory region, barriers, 256 TMEM
+// columns and unit sequence - "virtual CTA" 2 blockIdx + slot), which lets the two softmax groups TAKE TURNS on the SFU:
+// two independent CTAs fall into lockstep (both exponentiate - at half rate each -, then both sit in tcgen05.ld /
+// barrier latencies with the SFU idle); with turns one group's 32-exponential segment runs at the full SFU rate while
+// the other group is in its loads / max / exchange.  The turn is a shared-memory word handed over by the eighth
+// release of a group; a group whose partner is outside its tile loop (epilogue, finished) does not wait, and every
+// wait is bounded, so the scheme can only change timing.
+template <bool BF16, bool POLY, int SLOTS>
+__global__ void __launch_bounds__(kAttnThreads * SLOTS, 3 - SLOTS)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKx,
                const __grid_constant__ CUtensorMap tmVx, const AttnTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ int alt_turn, alt_rel[2], alt_present[2];
+  const int warp_g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = SLOTS == 2 ? warp_g / kWarpsPerSlot : 0;
+  const int warp = warp_g - slot * kWarpsPerSlot;                      // role index inside the pipeline
+  const int vcta = blockIdx.x * SLOTS + slot, vgrid = gridDim.x * SLOTS;   // this pipeline among all of the grid
+  uint8_t* smem0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem0 + slot * kSlotSmem;
   uint8_t* sQ = smem;                                   // [16 KB] (single: the last Q K^T of a unit is issued a whole
                                                         // tile before the unit ends, which is the time the next Q has to arrive)
   uint8_t* sK = smem + kQBytes;                         // [kStagesKV][16 KB]
@@ -307,13 +327,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* o_free = o_done + 1;           // softmax -> MMA: O of the previous unit has been read (256 arrivals)
   uint64_t* x_full = o_free + 1;           // [2] TMA -> softmax: leftover-key K / V rows of the unit have landed
   uint64_t* x_empty = x_full + 2;          // [2] softmax -> TMA: they have been used (256 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_empty + 2);
+  // the TMEM base address lands in slot 0's region (one allocation of SLOTS x 256 columns)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(x_empty + 2) - slot * kSlotSmem);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.n_tiles;           // tensor-core key tiles; the n_extra leftover keys are added in the epilogue
   const int n_extra = p.n_extra;
 
   if (threadIdx.x == 0) {
+    alt_turn = 0;
+    alt_rel[0] = alt_rel[1] = 0;
+    alt_present[0] = alt_present[1] = 0;
+  }
+  if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -336,7 +361,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_init(o_done, 1);
     mbar_init(o_free, kSoftmaxThreads);
     fence_mbar_init();
-    if (p.dbg) {   // per-CTA residency record: SM id, start time (ns)
+    if (p.dbg && slot == 0) {   // per-CTA residency record: SM id, start time (ns)
       uint32_t smid;
       unsigned long long t;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -345,14 +370,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       p.dbg[192 + blockIdx.x * 4 + 2] = t;
     }
   }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemColsAttn);
+  if (warp_g == 2) {
+    tmem_alloc(tmem_slot, kTmemColsAttn * SLOTS);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot + slot * kTmemColsAttn;
   pdl_launch_dependents();
   pdl_wait();
 
@@ -369,7 +394,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // ---------------------------------------------------------------- TMA producer
       int g = 0;   // global key-tile counter of this CTA
       int i = 0;   // local unit counter
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+      for (int u = vcta; u < p.n_units; u += vgrid, ++i) {
         int b, h, q0;
         unit_coords(u, b, h, q0);
         const int hk = h / p.group;
@@ -399,7 +424,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (elect_one()) {
       // ------------------------------------------------- MMA issuer 1: S = Q K_j^T
       int g = 0, i = 0;
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+      for (int u = vcta; u < p.n_units; u += vgrid, ++i) {
         const uint32_t q_addr = smem_u32(sQ);
         mbar_wait(q_full, i & 1);
         tc_fence_after();
@@ -427,7 +452,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // ------------------------------------------------- MMA issuer 2: O += P V_j
       constexpr uint32_t idesc_pv = make_idesc_f16(kQ, kD, BF16, /*b_mn_major=*/true);
       int g = 0, i = 0;
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+      for (int u = vcta; u < p.n_units; u += vgrid, ++i) {
         for (int j = 0; j < n_tiles; ++j, ++g) {
           const int st = g % kStagesKV;
           mbar_wait(&v_full[st], (g / kStagesKV) & 1);
@@ -457,7 +482,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // ------------------------------------------------------- ragged query rows on CUDA cores
     if (p.n_rows > 0) {
       const int n_tasks = p.batch * p.H * p.n_rows;
-      for (int t = blockIdx.x; t < n_tasks; t += gridDim.x) {
+      for (int t = vcta; t < n_tasks; t += vgrid) {
         const int bh = t / p.n_rows, r = t - bh * p.n_rows;
         const int b = bh / p.H, h = bh - b * p.H;
         attn_row_path<BF16>(p, b, h, p.row0 + r, prow, lane);
@@ -474,13 +499,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t s_addr = t_lane + kColS, p_addr = t_lane + kColP, o_addr = t_lane + kColO;
     const float sc = p.scale_log2;
-    const bool trace = p.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
+    const bool trace = p.dbg != nullptr && vcta == 0 && warp == 4 && lane == 0;
     // exchange slot s: this thread writes xch[s][half][row] and reads xch[s][1 - half][row] after the pair barrier
     auto xput = [&](int slot, float v) { xch[(slot * 2 + half) * kQ + row] = v; };
     auto xget = [&](int slot) -> float { return xch[(slot * 2 + (half ^ 1)) * kQ + row]; };
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };   // the two warps of a quadrant
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q + 4 * slot) : "memory"); };   // the two warps of a quadrant
+    // turn-taking on the SFU between the two pipelines of the CTA (SLOTS == 2)
+    const bool alt = SLOTS == 2 && p.alternate != 0;
+    auto alt_acquire = [&]() {
+      if (alt) {
+        if (lane == 0) {
+          int spins = 0;
+          while (*reinterpret_cast<volatile int*>(&alt_turn) != slot &&
+                 *reinterpret_cast<volatile int*>(&alt_present[slot ^ 1]) > 0 && ++spins < kAltSpinMax) {
+          }
+        }
+        __syncwarp();
+      }
+    };
+    auto alt_release = [&]() {
+      if (alt && lane == 0) {
+        if ((atomicAdd(&alt_rel[slot], 1) & 7) == 7) *reinterpret_cast<volatile int*>(&alt_turn) = slot ^ 1;
+      }
+    };
     int g = 0, i = 0;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
+    for (int u = vcta; u < p.n_units; u += vgrid, ++i) {
       int b, h, q0;
       unit_coords(u, b, h, q0);
       const int hk = h / p.group;
@@ -515,6 +558,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         mbar_arrive(q_empty);            // this thread is done with Q
       }
       if (trace && g < 16) p.dbg[g * 12 + 2] = clock64();
+      if (alt && lane == 0 && n_tiles > 0) atomicAdd(&alt_present[slot], 1);
       for (int j = 0; j < n_tiles; ++j, ++g) {
         const int nk = min(kK, p.Nk - j * kK);
         const int c0 = 2 * half;                 // this thread's chunks of 32 keys: c0, c0 + 1
@@ -619,8 +663,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tmem_ld_wait();
           mx_raw = cmax(lim0);
           wait_p_free();
+          alt_acquire();
           sum = cexp_store(lim0, pa0);
         }
+        alt_release();                           // (every warp releases twice per tile, with or without valid keys)
         if (trace && g < 16) p.dbg[g * 12 + 3] = clock64();
         if (lim1 > 0) {
           tmem_ld_32x32(sa1, r);
@@ -637,10 +683,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           mbar_arrive(s_free);                   // this thread holds its last chunk in registers
           if (lim1 > 0) {
             wait_p_free();
+            alt_acquire();
             sum += cexp_store(lim1, pa1);
           }
+          alt_release();
         } else {
           wait_p_free();
+          alt_acquire();
           const float m_new = need ? mx_tile * sc : m_ref;
           const float f = ex2_approx(m_ref - m_new);   // 1 for rows that keep their reference
           m_ref = m_new;
@@ -652,6 +701,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             tmem_ld_wait();
             sum += cexp_store(lim0, pa0);
           }
+          alt_release();
           tc_fence_before();
           mbar_arrive(s_free);
           if (j > 0) {                           // each half rescales its 32 columns of O
@@ -676,6 +726,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       // ---- epilogue of the unit: (O + leftover keys) / l -> global; each half stores 32 of the 64 columns, in two
       // passes of 16 (the 80-register budget of a 384-thread CTA does not hold a 32-column row plus the extras)
+      if (alt && lane == 0 && n_tiles > 0) atomicSub(&alt_present[slot], 1);
       const int gt = g - 1;                      // trace row of the unit's last tile
       if (trace && gt >= 0 && gt < 16) p.dbg[gt * 12 + 5] = clock64();
       if (n_tiles == 0) {
@@ -756,9 +807,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     p.dbg[192 + blockIdx.x * 4 + 3] = t;
   }
-  if (warp == 2) {
+  if (warp_g == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemColsAttn);
+    tmem_dealloc(tmem_base, kTmemColsAttn * SLOTS);
   }
 }
 
@@ -808,7 +859,13 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
   const int rem = Nq % kQ;
   const int slots_all = 2 * device_sm_count();
   bool row_path = rem != 0 && rem <= kRowPathMax;
-  if (row_path) {
+  static int force_rows = -2;
+  if (force_rows == -2) {
+    const char* e = getenv("SATB_ATTN_ROWPATH");     // 0 / 1: force the partial tile / the CUDA-core rows (A-B switch)
+    force_rows = e ? (atoi(e) != 0) : -1;
+  }
+  if (row_path && force_rows == 0) row_path = false;
+  if (row_path && force_rows < 0) {
     const double unit_cycles = a.n_tiles * 2900.0 + 4500.0, row_cycles = 110.0 * Nk;
     const double units_per_cta = static_cast<double>(batch) * H * (Nq / kQ) / slots_all;
     const double rows_per_cta = std::ceil(static_cast<double>(batch) * H * rem / slots_all);
@@ -823,34 +880,46 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
   a.scale_log2 = (1.0f / sqrtf(64.0f)) * 1.4426950408889634f;
   a.dbg = dbg;
   const int row_tasks = batch * H * a.n_rows;
-  int grid = a.n_units > row_tasks ? a.n_units : row_tasks;
-  static int ctas_per_sm = -1;
+  int grid = a.n_units > row_tasks ? a.n_units : row_tasks;   // pipelines with work
+  static int ctas_per_sm = -1, n_slots = -1, alternate = -1;
   if (ctas_per_sm < 0) {
-    const char* e = getenv("SATB_ATTN_CTAS_PER_SM");   // 1: one CTA per SM (A/B measurement of the SFU sharing)
+    const char* e = getenv("SATB_ATTN_CTAS_PER_SM");   // 1: one pipeline per SM (A/B measurement of the SFU sharing)
     ctas_per_sm = (e && atoi(e) == 1) ? 1 : 2;
+    e = getenv("SATB_ATTN_SLOTS");                     // 1: two CTAs of one pipeline per SM; 2: one CTA of two pipelines
+    n_slots = e ? (atoi(e) == 1 ? 1 : 2) : kAttnSlotsDefault;
+    e = getenv("SATB_ATTN_ALT");                       // 0: the two pipelines of a CTA do not take turns on the SFU
+    alternate = e ? (atoi(e) != 0) : 1;
   }
+  a.alternate = alternate;
   const int slots = ctas_per_sm * device_sm_count();
   if (grid > slots) grid = slots;
   if (grid <= 0) return 0;
+  if (n_slots == 2) grid = (grid + 1) / 2;             // CTAs of two pipelines
   static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("SATB_ATTN_POLY");        // 0 / 1: A-B of the FMA-pipe exponentials
     poly = e ? (atoi(e) != 0) : kAttnPolyDefault;
   }
+  const int smem_bytes = attn_smem_bytes(n_slots);
   auto prepare = [&](auto kern) -> int {
-    SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     // two CTAs per SM need 2 x 98 KB: ask for the largest shared-memory carveout
     SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return 0;
   };
   auto go = [&](auto kern, PerDeviceOnce& once) -> int {
     if (once.first()) SATB_PROPAGATE(prepare(kern));
-    SATB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kAttnThreads), kAttnSmem, stream, tq, tk, tv, tkx, tvx, a));
+    SATB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kAttnThreads * n_slots), smem_bytes, stream, tq, tk, tv, tkx, tvx, a));
     return 0;
   };
-  static PerDeviceOnce o00, o01, o10, o11;
-  if (bf16) SATB_PROPAGATE(poly ? go(attn_tc_kernel<true, true>, o11) : go(attn_tc_kernel<true, false>, o10));
-  else SATB_PROPAGATE(poly ? go(attn_tc_kernel<false, true>, o01) : go(attn_tc_kernel<false, false>, o00));
+  static PerDeviceOnce o00, o01, o10, o11, t00, t01, t10, t11;
+  if (n_slots == 2) {
+    if (bf16) SATB_PROPAGATE(poly ? go(attn_tc_kernel<true, true, 2>, t11) : go(attn_tc_kernel<true, false, 2>, t10));
+    else SATB_PROPAGATE(poly ? go(attn_tc_kernel<false, true, 2>, t01) : go(attn_tc_kernel<false, false, 2>, t00));
+  } else {
+    if (bf16) SATB_PROPAGATE(poly ? go(attn_tc_kernel<true, true, 1>, o11) : go(attn_tc_kernel<true, false, 1>, o10));
+    else SATB_PROPAGATE(poly ? go(attn_tc_kernel<false, true, 1>, o01) : go(attn_tc_kernel<false, false, 1>, o00));
+  }
   count_launch();
   SATB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -859,7 +928,7 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
 // Debug: resident CTAs per SM the runtime reports for the attention kernel with `dyn_smem` bytes of dynamic shared
 // memory and the given carveout preference (percent, -1 = leave unchanged); tests / profiling only.
 int debug_attention_occupancy(int dyn_smem, int carveout_pct) {
-  auto kern = attn_tc_kernel<false, false>;
+  auto kern = attn_tc_kernel<false, false, 1>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem) != cudaSuccess) return -1;
   if (carveout_pct >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct);
   int nb = -1;

@@ -24,6 +24,11 @@
 
 namespace satb {
 
+// Order of the split-operand parts: the two small cross terms (lo, hi), (hi, lo) are accumulated FIRST, into a still
+// small accumulator, and the (hi, hi) chain last: the tensor core truncates when it aligns addends to the accumulator,
+// so adding 2^-11-sized terms to a full-sized sum costs about one accumulator ulp per k-step each.
+__device__ __forceinline__ int split_part(int idx, int n_parts) { return n_parts == 3 ? (idx == 2 ? 0 : idx + 1) : idx; }
+
 struct GemmShape {
   int L;            // rows per batch
   int batches;      // number of batches (1 for flat GEMMs)
@@ -163,7 +168,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         pre = num_kb < Cfg::kStages ? num_kb : Cfg::kStages;
         const int n0 = (static_cast<int>(blockIdx.x) / tiles_per_n) * BN;
         for (int kb = 0; kb < pre; ++kb) {
-          const int part = kb / kb_per_part, kbp = kb - part * kb_per_part;
+          const int pidx = kb / kb_per_part, kbp = kb - pidx * kb_per_part;
+          const int part = split_part(pidx, s.n_parts);
           const int tap = kbp / kb_per_tap;
           const int k0 = (kbp - tap * kb_per_tap) * kBlockK;
           mbar_expect_tx(&full_bar[kb], Cfg::kStage);
@@ -181,7 +187,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int m0 = (rem - batch * m_tiles) * kBlockM;
         const int n0 = nt * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int part = kb / kb_per_part, kbp = kb - part * kb_per_part;
+          const int pidx = kb / kb_per_part, kbp = kb - pidx * kb_per_part;
+          const int part = split_part(pidx, s.n_parts);
           const int tap = kbp / kb_per_tap;
           const int k0 = (kbp - tap * kb_per_tap) * kBlockK;
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -396,7 +403,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         pre = num_kb < Cfg::kStages ? num_kb : Cfg::kStages;
         const int n0 = (cluster_id / tiles_per_n) * BN + rank * (BN / 2);
         for (int kb = 0; kb < pre; ++kb) {
-          const int part = kb / kb_per_part, kbp = kb - part * kb_per_part;
+          const int pidx = kb / kb_per_part, kbp = kb - pidx * kb_per_part;
+          const int part = split_part(pidx, s.n_parts);
           const int tap = kbp / kb_per_tap;
           const int k0 = (kbp - tap * kb_per_tap) * kBlockK;
           if (rank == 0) mbar_expect_tx(&full_bar[kb], 2 * Cfg::kStage);
@@ -414,7 +422,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int m0 = (rem - batch * m_tiles) * 2 * kBlockM + rank * kBlockM;
         const int n0 = nt * BN + rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int part = kb / kb_per_part, kbp = kb - part * kb_per_part;
+          const int pidx = kb / kb_per_part, kbp = kb - pidx * kb_per_part;
+          const int part = split_part(pidx, s.n_parts);
           const int tap = kbp / kb_per_tap;
           const int k0 = (kbp - tap * kb_per_tap) * kBlockK;
           mbar_wait(&empty_bar[stage], phase ^ 1);

@@ -193,14 +193,14 @@ def test_full_size_decoder_is_shift_equivariant_and_deterministic():
     assert rel_l2(got.cpu(), ref.cpu()) < 1e-5
 
 
-def test_full_sao_decoder_split_operand_mode_adds_20_db():
-    """operand_dtype="fp16x3" (every convolution product as (hi, hi) + (lo, hi) + (hi, lo) on the tensor cores, fp32
+def test_full_sao_decoder_split_operand_mode_reaches_70_db():
+    """operand_dtype="fp16x3" (every convolution product as (lo, hi) + (hi, lo) + (hi, hi) on the tensor cores, fp32
     skip stream): the SA-Open decoder on 32 latents against the fp32 oracle - the reference runs these convolutions in
-    strict fp32 (inference/generation.py:165-166).  Measured 59.7 dB audio-domain SNR where the plain fp16 mode sits
-    at 40.1 dB on the same synthetic weights; what remains is the fp32 accumulation of the tensor cores themselves
-    (~1e-5 per 7168-term convolution, the same figure tests/test_gpu_primitives.py sees for a plain GEMM, amplified
-    ~20x by the Snake slopes of the synthetic weights over 37 layers) - an accurate sinf instead of the SFU sine
-    changed nothing.  Gate: >= 58 dB and >= 15 dB better than fp16 (SURVEY.md 7.1b suggests 60)."""
+    strict fp32 (inference/generation.py:165-166).  Measured 72.9 dB audio-domain SNR (encoder: 82.9 dB) where the
+    plain fp16 mode sits at 40.1 dB on the same synthetic weights.  The ORDER of the three parts matters: the tensor
+    core truncates addends when it aligns them to the accumulator, so the two 2^-11-sized cross terms are accumulated
+    first, into a still small sum; with (hi, hi) first the same arithmetic gave 59.7 dB.  An accurate sinf instead of
+    the SFU sine changed nothing.  Gate: >= 68 dB and >= 25 dB better than fp16 (SURVEY.md 7.1b asks for 60)."""
     import math
     from oracle import oobleck_oracle as oo
     from stable_audio_tools.models.autoencoders import OobleckDecoder, OobleckEncoder
@@ -216,8 +216,8 @@ def test_full_sao_decoder_split_operand_mode_adds_20_db():
         y = dec.cuda().eval()(z.cuda()).cpu()
         snr[mode] = -20.0 * math.log10(rel_l2(y, ref))
     print("decoder SNR dB:", snr)
-    assert snr["fp16x3"] >= 58.0, snr
-    assert snr["fp16x3"] > snr["fp16"] + 15.0, snr
+    assert snr["fp16x3"] >= 68.0, snr
+    assert snr["fp16x3"] > snr["fp16"] + 25.0, snr
     # the encoder goes through the same convolution code (strided taps, CUDA-core input conv with its lo copy)
     ecfg = dict(SAO_VAE, in_channels=2, latent_dim=128)
     esd = oo.make_oobleck_weights(oo.encoder_param_shapes(ecfg), seed=12)
@@ -228,4 +228,4 @@ def test_full_sao_decoder_split_operand_mode_adds_20_db():
     enc.load_state_dict(esd)
     esnr = -20.0 * math.log10(rel_l2(enc.cuda().eval()(a.cuda()).cpu(), eref))
     print("encoder SNR dB (fp16x3):", esnr)
-    assert esnr >= 58.0, esnr
+    assert esnr >= 68.0, esnr
