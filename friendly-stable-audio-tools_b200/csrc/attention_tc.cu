@@ -1,33 +1,35 @@
 // tcgen05 attention forward, head dim 64, no mask, non-causal, optional GQA:
 //   O = softmax(Q K^T / sqrt(64)) V      (reference models/transformer.py:496-536)
 //
-// Persistent kernel, two CTAs of 384 threads per SM (2 x 256 TMEM columns, 2 x 86 KB shared memory).  A work unit is
+// Persistent kernel, two CTAs of 384 threads per SM (2 x 256 TMEM columns, 2 x 111 KB shared memory).  A work unit is
 // 128 query rows of one (batch item, head); CTA c processes units c, c + grid, ... without re-initialising anything.
 // Keys are processed in tiles of 128:
-//   warp 0 (one thread)  TMA producer: Q of the unit, K / V tiles (2-stage rings)
+//   warp 0 (one thread)  TMA producer: Q of the unit, K / V tiles (2-stage rings), the unit's leftover-key rows
 //   warp 1 (one thread)  S = Q K_j^T -> TMEM (tcgen05.mma, smem operands) as soon as S has been read out
 //   warp 3 (one thread)  O += P V_j (A = P from TMEM, B = V tile addressed MN-major)
 //   warps 4-11           softmax: warps w and w + 4 own the same 32 query rows (TMEM lane quadrant w % 4) and split the
-//                        128 key columns of a tile; per 32-column chunk: tcgen05.ld -> row max -> P = exp2(S c - m_ref)
-//                        -> packed 16-bit pairs back to TMEM; row sums in fp32 registers.
+//                        128 key columns of a tile; per 16-column chunk: tcgen05.ld -> row max -> P = exp2(S c - m_ref)
+//                        -> packed 16-bit pairs back to TMEM, with the next chunk's load in flight; row sums in fp32.
 //   warp 2               TMEM allocator; afterwards the CUDA-core path for ragged query rows (below)
 // TMEM columns: S [0,128)  P [128,192)  O [192,256).
-// Why eight softmax warps: the softmax is bound by the SFU (16 ex2 / clk / SM = one MUFU.EX2 warp instruction per
-// 8 cycles and scheduler; 202 M exponentials per SA-Open layer) only if every scheduler always has a warp with
-// exponentials to issue.  A lone warp per scheduler reaches 12.8 cycles per MUFU (in-order issue behind the FFMA2 /
-// F2FP / FADD2 of its own stream) and spends as long again in tcgen05.ld / st / mbarrier latencies per tile; with
-// two such warps (two CTAs of four softmax warps) the CTAs fall into lockstep - both exponentiate, then both wait -
-// (measured, profiles/r02_attention_*.txt).  Four warps per scheduler cover those latencies.
+// What bounds it (measured, profiles/README.md): per 128 x 128 tile the SFU needs 1024 cycles (16 ex2 / clk / SM) and
+// tcgen05.ld as many (64 B / clk / SM for the fp32 S tile); with eight softmax warps per CTA and two CTAs per SM a tile
+// takes ~1400 cycles of the SM.  Around the tiles: a unit of 8 key tiles pays ~2500 cycles for its boundary (last P V,
+// normalise, first-tile max), and 1536 units on 296 CTAs are 5.2 rounds of work in 6.
 // O stays in TMEM for the whole unit: the reference max m_ref only moves when a tile's row max exceeds it by more
 // than 2^8 (lazy rescale: exponentials stay <= 256, sums in fp32), so the O rescale (TMEM load-scale-store) and the
 // recomputation of that tile's P are rare.
+// The normalised output tile is staged in shared memory and leaves with one TMA store under the next unit (per-thread
+// 16-byte stores to 3 KB-strided rows kept the load/store unit busy for ~2700 cycles per unit).
 //
 // Ragged shapes (1025 = 8 * 128 + 1 tokens: the prepended conditioning token):
 //   * leftover KEYS (Nk % 128 <= kExtraMax) do not get a tile of their own - a whole pipeline step for one column -:
-//     every softmax thread computes its row's score against them on CUDA cores (q from the Q tile in shared memory)
-//     and adds exp2(.) v to its O row in the epilogue, in fp32;
+//     their scores S_x = Q K_x^T come from one 16-column MMA chain into the first columns of the P region while it is
+//     idle between two units; every softmax thread keeps exp2(s_x - m_ref) in fp32 registers (part of the first
+//     tile's reference max, scaled along in a rescale) and adds p_x v_x to its O row in the epilogue;
 //   * leftover QUERY rows (Nq % 128 <= kRowPathMax) are computed by warp 2 on CUDA cores (one warp per row:
-//     eight lanes per key, online softmax over blocks of 1024 keys), concurrently with the tensor-core pipeline.
+//     eight lanes per key, online softmax over blocks of 512 keys), concurrently with the tensor-core pipeline -
+//     unless the batch is so small that a partial ninth query tile is cheaper (cost model in launch_attention_tc).
 #include "common.cuh"
 #include "gemm.cuh"
 #include "kernels.h"
@@ -45,21 +47,19 @@ constexpr int kD = 64;         // head dim
 constexpr int kStagesKV = 2;
 constexpr int kQBytes = kQ * kD * 2;                         // 16 KB
 constexpr int kKVBytes = kK * kD * 2;                        // 16 KB
-constexpr int kRowChunk = 1024;                              // keys per block of the CUDA-core row path
+constexpr int kRowChunk = 512;                               // keys per block of the CUDA-core row path
 constexpr int kRowBatch = 8;                                 // independent 16-byte loads in flight per lane (row path)
 constexpr int kRowPathMax = 2;                               // Nq % 128 <= this: those rows take the row path
 constexpr int kAttnThreads = 384;                            // 4 control warps + 8 softmax warps
 constexpr int kSoftmaxThreads = 256;
 constexpr int kAttnPolyDefault = 0;                          // see SATB_ATTN_POLY
-constexpr int kAttnSlotsDefault = 2;                         // see SATB_ATTN_SLOTS
 constexpr int kExtraMax = 2;                                 // Nk % 128 <= this: those keys are added in the epilogue
 constexpr int kXRows = 16;                                   // rows of the leftover-key K / V tiles (TMA box)
 constexpr int kXBytes = kXRows * kD * 2;                     // 2 KB
-// shared memory of one pipeline ("slot"): Q, K / V rings, leftover-key boxes, row-path scratch, exchange slots, barriers
-constexpr int kSlotSmem = (kQBytes + 2 * kStagesKV * kKVBytes + 4 * kXBytes + kRowChunk * 4 + 4 * 2 * kQ * 4 + 256 + 1023) & ~1023;   // 97 KB
-constexpr int attn_smem_bytes(int slots) { return slots * kSlotSmem + 1024; }
-constexpr int kWarpsPerSlot = kAttnThreads / 32;
-constexpr int kAltSpinMax = 400;                             // safety valve of the turn-taking below (never a correctness matter)
+constexpr int kOBytes = kQ * kD * 2;                         // 16 KB: output tile staged for the TMA store
+// Q, K / V rings, output staging, leftover-key boxes, row-path scratch, exchange slots, barriers, alignment slack:
+// 111.25 KB, two CTAs per SM
+constexpr int kAttnSmem = kQBytes + 2 * kStagesKV * kKVBytes + kOBytes + 4 * kXBytes + kRowChunk * 4 + 4 * 2 * kQ * 4 + 256 + 1024;
 constexpr int kTmemColsAttn = 256;
 constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;
 constexpr float kRescaleThreshold = 8.0f;                    // log2 units
@@ -72,11 +72,11 @@ struct AttnTcArgs {
   int n_tiles, n_extra;      // key tiles on the tensor cores; leftover keys (Nk - 128 n_tiles <= kExtraMax) added in the epilogue
   int n_qt;                  // tensor-core query tiles per (item, head)
   int n_units;               // batch * H * n_qt
+  int step_bh, step_qt;      // grid / n_qt, grid % n_qt: the (item-head, query tile) step between a CTA's consecutive units
   int row0, n_rows;          // rows [row0, row0 + n_rows) of every (item, head) take the CUDA-core path
   const uint16_t *q, *k, *v; // raw pointers for the row path
   int64_t ldq, ldk, ldv, q_bs, k_bs, v_bs;
   float scale_log2;
-  int alternate;             // SLOTS == 2: the two pipelines of a CTA take turns on the SFU (see attn_tc_kernel)
   unsigned long long* dbg;   // optional clock64 trace of CTA 0's first softmax warp (tests / profiles only)
 };
 
@@ -92,14 +92,9 @@ __device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t smem_addr) 
   return d;
 }
 
+// (volatile: a run of these stays in program order.  Left free, the compiler hoists all sixteen exponentials of a chunk
+// above their consumers, which costs ~90 bytes of spills at the 80-register budget and 5 % of the kernel, measured.)
 __device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// same instruction, but volatile: the compiler keeps a run of these in program order (see cexp below)
-__device__ __forceinline__ float ex2_ordered(float x) {
   float y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
@@ -283,38 +278,27 @@ __device__ void attn_row_path(const AttnTcArgs& p, int b, int h, int row, float*
 }
 
 // POLY: every fourth pair of exponentials of a full chunk goes through ex2_poly2 (FMA / ALU pipes) instead of the SFU
-// SLOTS: pipelines per CTA.  1: a CTA of 384 threads is one pipeline, two CTAs share an SM.  2: ONE CTA of 768 threads
-// per SM runs two complete pipelines (warps 0-11 and 12-23, each with its own shared-memory region, barriers, 256 TMEM
-// columns and unit sequence - "virtual CTA" 2 blockIdx + slot), which lets the two softmax groups TAKE TURNS on the SFU:
-// two independent CTAs fall into lockstep (both exponentiate - at half rate each -, then both sit in tcgen05.ld /
-// barrier latencies with the SFU idle); with turns one group's 32-exponential segment runs at the full SFU rate while
-// the other group is in its loads / max / exchange.  The turn is a shared-memory word handed over by the eighth
-// release of a group; a group whose partner is outside its tile loop (epilogue, finished) does not wait, and every
-// wait is bounded, so the scheme can only change timing.
-template <bool BF16, bool POLY, int SLOTS>
-__global__ void __launch_bounds__(kAttnThreads * SLOTS, 3 - SLOTS)
+template <bool BF16, bool POLY>
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKx,
-               const __grid_constant__ CUtensorMap tmVx, const AttnTcArgs p) {
+               const __grid_constant__ CUtensorMap tmVx, const __grid_constant__ CUtensorMap tmO, const AttnTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ int alt_turn, alt_rel[2], alt_present[2];
-  const int warp_g = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slot = SLOTS == 2 ? warp_g / kWarpsPerSlot : 0;
-  const int warp = warp_g - slot * kWarpsPerSlot;                      // role index inside the pipeline
-  const int vcta = blockIdx.x * SLOTS + slot, vgrid = gridDim.x * SLOTS;   // this pipeline among all of the grid
-  uint8_t* smem0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem = smem0 + slot * kSlotSmem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (an offset added to the array keeps the shared address space visible to the compiler: LDS / STS, not generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                                   // [16 KB] (single: the last Q K^T of a unit is issued a whole
                                                         // tile before the unit ends, which is the time the next Q has to arrive)
   uint8_t* sK = smem + kQBytes;                         // [kStagesKV][16 KB]
   uint8_t* sV = sK + kStagesKV * kKVBytes;
-  uint8_t* sX = sV + kStagesKV * kKVBytes;              // [2 units][K | V][2 KB] leftover-key rows (16-row TMA boxes)
+  uint8_t* sO = sV + kStagesKV * kKVBytes;              // [16 KB] normalised output tile (128B-swizzled rows) for the TMA store
+  uint8_t* sX = sO + kOBytes;                           // [2 units][K | V][2 KB] leftover-key rows (16-row TMA boxes)
   float* prow = reinterpret_cast<float*>(sX + 4 * kXBytes);            // [kRowChunk] row-path scratch
   float* xch = prow + kRowChunk;                        // [4][2][128] exchange between the two column halves of a row:
                                                         // slots 0 / 1 = tile parity, 2 = first-tile max, 3 = row sums
   uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 4 * 2 * kQ);
   uint64_t* q_full = bars;                 // TMA -> MMA / softmax: Q of the unit has landed
-  uint64_t* q_empty = bars + 1;            // MMA (+ softmax, when it reads Q for leftover keys) -> TMA
+  uint64_t* q_empty = bars + 1;            // MMA -> TMA: every MMA reading Q has retired
   uint64_t* k_full = bars + 2;             // [kStagesKV]
   uint64_t* k_empty = k_full + kStagesKV;
   uint64_t* v_full = k_empty + kStagesKV;
@@ -327,23 +311,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* o_free = o_done + 1;           // softmax -> MMA: O of the previous unit has been read (256 arrivals)
   uint64_t* x_full = o_free + 1;           // [2] TMA -> softmax: leftover-key K / V rows of the unit have landed
   uint64_t* x_empty = x_full + 2;          // [2] softmax -> TMA: they have been used (256 arrivals)
-  // the TMEM base address lands in slot 0's region (one allocation of SLOTS x 256 columns)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(x_empty + 2) - slot * kSlotSmem);
+  uint64_t* sx_full = x_empty + 2;         // MMA -> softmax: P[0,16) holds Q K_x^T of the unit's leftover keys
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sx_full + 1);
 
   const int n_tiles = p.n_tiles;           // tensor-core key tiles; the n_extra leftover keys are added in the epilogue
   const int n_extra = p.n_extra;
 
   if (threadIdx.x == 0) {
-    alt_turn = 0;
-    alt_rel[0] = alt_rel[1] = 0;
-    alt_present[0] = alt_present[1] = 0;
-  }
-  if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    mbar_init(q_empty, n_extra > 0 ? 1 + kSoftmaxThreads : 1);
+    mbar_init(q_empty, 1);
+    mbar_init(sx_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&x_full[i], 1);
       mbar_init(&x_empty[i], kSoftmaxThreads);
@@ -361,7 +341,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_init(o_done, 1);
     mbar_init(o_free, kSoftmaxThreads);
     fence_mbar_init();
-    if (p.dbg && slot == 0) {   // per-CTA residency record: SM id, start time (ns)
+    if (p.dbg) {   // per-CTA residency record: SM id, start time (ns)
       uint32_t smid;
       unsigned long long t;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -370,23 +350,44 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       p.dbg[192 + blockIdx.x * 4 + 2] = t;
     }
   }
-  if (warp_g == 2) {
-    tmem_alloc(tmem_slot, kTmemColsAttn * SLOTS);
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemColsAttn);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot + slot * kTmemColsAttn;
+  const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   pdl_wait();
 
   // unit u -> (item b, head h, query tile qt); consecutive units share (b, h), i.e. their K / V tiles in L2
-  auto unit_coords = [&](int u, int& b, int& h, int& q0) {
-    const int bh = u / p.n_qt;
-    q0 = (u - bh * p.n_qt) * kQ;
-    b = bh / p.H;
-    h = bh - b * p.H;
+  // The CTA walks units blockIdx, blockIdx + grid, ...: the two divisions are done once, every further unit is reached by
+  // adding the precomputed (grid / n_qt, grid % n_qt) step (the divisions cost ~400 cycles on the softmax warps' path).
+  struct Unit { int u, b, h, q0; };
+  auto unit_first = [&]() -> Unit {
+    Unit t;
+    t.u = blockIdx.x;
+    const int nq = max(p.n_qt, 1);
+    const int bh = t.u / nq;
+    t.q0 = (t.u - bh * nq) * kQ;
+    t.b = bh / p.H;
+    t.h = bh - t.b * p.H;
+    return t;
+  };
+  auto unit_next = [&](Unit& t) {
+    t.u += gridDim.x;
+    t.q0 += p.step_qt * kQ;
+    int dh = p.step_bh;
+    if (t.q0 >= p.n_qt * kQ) {
+      t.q0 -= p.n_qt * kQ;
+      ++dh;
+    }
+    t.h += dh;
+    while (t.h >= p.H) {
+      t.h -= p.H;
+      ++t.b;
+    }
   };
 
   if (warp == 0) {
@@ -394,9 +395,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // ---------------------------------------------------------------- TMA producer
       int g = 0;   // global key-tile counter of this CTA
       int i = 0;   // local unit counter
-      for (int u = vcta; u < p.n_units; u += vgrid, ++i) {
-        int b, h, q0;
-        unit_coords(u, b, h, q0);
+      for (Unit t = unit_first(); t.u < p.n_units; unit_next(t), ++i) {
+        const int b = t.b, h = t.h, q0 = t.q0;
         const int hk = h / p.group;
         mbar_wait(q_empty, (i & 1) ^ 1);
         mbar_expect_tx(q_full, kQBytes);
@@ -424,10 +424,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (elect_one()) {
       // ------------------------------------------------- MMA issuer 1: S = Q K_j^T
       int g = 0, i = 0;
-      for (int u = vcta; u < p.n_units; u += vgrid, ++i) {
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
         const uint32_t q_addr = smem_u32(sQ);
         mbar_wait(q_full, i & 1);
         tc_fence_after();
+        if (n_extra > 0) {
+          // S_x = Q K_x^T for the unit's leftover keys: one 16-column MMA chain into the first 16 columns of the P
+          // region, which is idle between the previous unit's last P V and this unit's first P store (rows past Nk of
+          // the 16-row box are zero-filled by the TMA; the softmax reads columns 0 .. n_extra - 1 only)
+          mbar_wait(&x_full[i & 1], (i >> 1) & 1);
+          if (i >= 1 && n_tiles > 0) mbar_wait(o_done, (i - 1) & 1);   // (one phase per unit: p_free's parity would alias)
+          tc_fence_after();
+          const uint32_t idesc = make_idesc_f16(kQ, kXRows, BF16);
+          const uint32_t kx_addr = smem_u32(sX + (i & 1) * 2 * kXBytes);
+#pragma unroll
+          for (int ks = 0; ks < kD / 16; ++ks)
+            umma_f16_ss(tmem_base + kColP, make_desc_kmajor_sw128(q_addr + ks * 32),
+                        make_desc_kmajor_sw128(kx_addr + ks * 32), idesc, ks != 0);
+          umma_commit(sx_full);
+        }
         for (int j = 0; j < n_tiles; ++j, ++g) {
           const int st = g % kStagesKV;
           mbar_wait(&k_full[st], (g / kStagesKV) & 1);
@@ -444,7 +459,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           umma_commit(&k_empty[st]);   // the K tile is free as soon as these MMAs retire
           umma_commit(s_full);
         }
-        umma_commit(q_empty);          // every Q K^T of this unit has retired (immediately, if there was none)
+        umma_commit(q_empty);          // every MMA reading Q has retired (immediately, if there was none)
       }
     }
   } else if (warp == 3) {
@@ -452,7 +467,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // ------------------------------------------------- MMA issuer 2: O += P V_j
       constexpr uint32_t idesc_pv = make_idesc_f16(kQ, kD, BF16, /*b_mn_major=*/true);
       int g = 0, i = 0;
-      for (int u = vcta; u < p.n_units; u += vgrid, ++i) {
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++i) {
         for (int j = 0; j < n_tiles; ++j, ++g) {
           const int st = g % kStagesKV;
           mbar_wait(&v_full[st], (g / kStagesKV) & 1);
@@ -482,7 +497,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // ------------------------------------------------------- ragged query rows on CUDA cores
     if (p.n_rows > 0) {
       const int n_tasks = p.batch * p.H * p.n_rows;
-      for (int t = vcta; t < n_tasks; t += vgrid) {
+      for (int t = blockIdx.x; t < n_tasks; t += gridDim.x) {
         const int bh = t / p.n_rows, r = t - bh * p.n_rows;
         const int b = bh / p.H, h = bh - b * p.H;
         attn_row_path<BF16>(p, b, h, p.row0 + r, prow, lane);
@@ -499,157 +514,145 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t s_addr = t_lane + kColS, p_addr = t_lane + kColP, o_addr = t_lane + kColO;
     const float sc = p.scale_log2;
-    const bool trace = p.dbg != nullptr && vcta == 0 && warp == 4 && lane == 0;
+    const bool trace = p.dbg != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0;
     // exchange slot s: this thread writes xch[s][half][row] and reads xch[s][1 - half][row] after the pair barrier
     auto xput = [&](int slot, float v) { xch[(slot * 2 + half) * kQ + row] = v; };
     auto xget = [&](int slot) -> float { return xch[(slot * 2 + (half ^ 1)) * kQ + row]; };
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q + 4 * slot) : "memory"); };   // the two warps of a quadrant
-    // turn-taking on the SFU between the two pipelines of the CTA (SLOTS == 2)
-    const bool alt = SLOTS == 2 && p.alternate != 0;
-    auto alt_acquire = [&]() {
-      if (alt) {
-        if (lane == 0) {
-          int spins = 0;
-          while (*reinterpret_cast<volatile int*>(&alt_turn) != slot &&
-                 *reinterpret_cast<volatile int*>(&alt_present[slot ^ 1]) > 0 && ++spins < kAltSpinMax) {
-          }
-        }
-        __syncwarp();
-      }
-    };
-    auto alt_release = [&]() {
-      if (alt && lane == 0) {
-        if ((atomicAdd(&alt_rel[slot], 1) & 7) == 7) *reinterpret_cast<volatile int*>(&alt_turn) = slot ^ 1;
-      }
-    };
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };   // the two warps of a quadrant
+    auto softmax_sync = [&]() { asm volatile("bar.sync 5, 256;" ::: "memory"); };             // all eight softmax warps
     int g = 0, i = 0;
-    for (int u = vcta; u < p.n_units; u += vgrid, ++i) {
-      int b, h, q0;
-      unit_coords(u, b, h, q0);
-      const int hk = h / p.group;
+    for (Unit t = unit_first(); t.u < p.n_units; unit_next(t), ++i) {
+      const int b = t.b, h = t.h, q0 = t.q0;
       float m_ref = -INFINITY, l = 0.f;
-      // ---- leftover keys (Nk % 128 <= kExtraMax): their scores on CUDA cores, from the Q tile in shared memory
-      float s_x[kExtraMax];
+      const uint8_t* xk = sX + (i & 1) * 2 * kXBytes;   // K rows of the unit's leftover keys; V rows follow at + kXBytes
+      // ---- leftover keys (Nk % 128 <= kExtraMax): their scores come from a 16-column MMA (P[0,16), see the MMA issuer);
+      // they count in the first tile's reference max, their exponentials p_x are kept in fp32 registers (scaled along
+      // in the rare rescale) and p_x V_x is added to the O row in the epilogue.
+      float s_x[kExtraMax], p_x[kExtraMax];
 #pragma unroll
-      for (int e = 0; e < kExtraMax; ++e) s_x[e] = -INFINITY;
-      const uint8_t* xk = sX + (i & 1) * 2 * kXBytes;   // K rows of the leftover keys; V rows follow at + kXBytes
+      for (int e = 0; e < kExtraMax; ++e) {
+        s_x[e] = -INFINITY;
+        p_x[e] = 0.f;
+      }
       if (n_extra > 0) {
-        mbar_spin(q_full, i & 1);
-        mbar_spin(&x_full[i & 1], (i >> 1) & 1);
+        uint32_t sx[2];
+        mbar_spin(sx_full, i & 1);
+        tc_fence_after();
+        tmem_ld_32x2(p_addr, sx);
+        tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < kExtraMax; ++e) {
-          if (e < n_extra) {
-            float acc = 0.f;
-#pragma unroll 2
-            for (int c = 0; c < kD / 8; ++c) {
-              // 128B-swizzled K-major tiles: 16-byte chunk c of row r sits at chunk position c ^ (r % 8)
-              const uint4 qv = *reinterpret_cast<const uint4*>(sQ + row * 128 + ((c ^ (row & 7)) << 4));
-              const uint4 kv = *reinterpret_cast<const uint4*>(xk + e * 128 + ((c ^ e) << 4));   // same address in every lane
-              const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w}, kw[4] = {kv.x, kv.y, kv.z, kv.w};
-#pragma unroll
-              for (int d = 0; d < 4; ++d) {
-                const float2 a = Op16<BF16>::unpack(qw[d]), bb = Op16<BF16>::unpack(kw[d]);
-                acc = fmaf(a.x, bb.x, fmaf(a.y, bb.y, acc));
-              }
-            }
-            s_x[e] = acc;
-          }
-        }
-        mbar_arrive(q_empty);            // this thread is done with Q
+        for (int e = 0; e < kExtraMax; ++e)
+          if (e < n_extra) s_x[e] = __uint_as_float(sx[e]);
       }
       if (trace && g < 16) p.dbg[g * 12 + 2] = clock64();
-      if (alt && lane == 0 && n_tiles > 0) atomicAdd(&alt_present[slot], 1);
       for (int j = 0; j < n_tiles; ++j, ++g) {
         const int nk = min(kK, p.Nk - j * kK);
-        const int c0 = 2 * half;                 // this thread's chunks of 32 keys: c0, c0 + 1
-        const int lim0 = nk - c0 * 32, lim1 = lim0 - 32;   // valid keys in them (may be <= 0)
         if (trace && g < 16) p.dbg[g * 12 + 0] = clock64();
         mbar_spin(s_full, g & 1);
         tc_fence_after();
         if (trace && g < 16) p.dbg[g * 12 + 1] = clock64();
-        uint32_t r[32];
-        auto cmax = [&](int lim) -> float {      // raw max of the valid columns of the chunk in r[]
-          if (lim >= 32) {
-            float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
-#pragma unroll
-            for (int e = 4; e < 28; e += 8) {
-              m0 = fmaxf(m0, fmaxf(__uint_as_float(r[e]), __uint_as_float(r[e + 1])));
-              m1 = fmaxf(m1, fmaxf(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])));
-              m2 = fmaxf(m2, fmaxf(__uint_as_float(r[e + 4]), __uint_as_float(r[e + 5])));
-              m3 = fmaxf(m3, fmaxf(__uint_as_float(r[e + 6]), __uint_as_float(r[e + 7])));
-            }
-            m0 = fmaxf(m0, fmaxf(__uint_as_float(r[28]), __uint_as_float(r[29])));
-            m1 = fmaxf(m1, fmaxf(__uint_as_float(r[30]), __uint_as_float(r[31])));
-            return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-          }
-          float mx = -INFINITY;
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (e < lim) mx = fmaxf(mx, __uint_as_float(r[e]));
-          return mx;
+        // This thread's 64 key columns of the tile, in four chunks of 16.  tcgen05.ld moves 64 B per clock and SM
+        // (a 128 x 128 fp32 S tile = 1024 clocks, as long as its 16 K exponentials take on the SFU), so the load of
+        // chunk c + 1 is in flight while chunk c is exponentiated: ra / rb alternate, one load outstanding at a time
+        // (tcgen05.wait::ld waits for all of a thread's loads).
+        const int cbase = 64 * half;
+        const int lim = nk - cbase;              // valid key columns among the 64 (<= 0: none)
+        const uint32_t sa = s_addr + cbase, pa = p_addr + cbase / 2;
+        uint32_t ra[16], rb[16];
+        auto max16 = [&](const uint32_t (&r)[16], float m) -> float {
+          float m0 = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), m1 = fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3]));
+          float m2 = fmaxf(__uint_as_float(r[4]), __uint_as_float(r[5])), m3 = fmaxf(__uint_as_float(r[6]), __uint_as_float(r[7]));
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(r[8]), __uint_as_float(r[9])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(r[10]), __uint_as_float(r[11])));
+          m2 = fmaxf(m2, fmaxf(__uint_as_float(r[12]), __uint_as_float(r[13])));
+          m3 = fmaxf(m3, fmaxf(__uint_as_float(r[14]), __uint_as_float(r[15])));
+          return fmaxf(fmaxf(m, fmaxf(m0, m1)), fmaxf(m2, m3));
         };
-        // P chunk = exp2(S c - m_ref) of r[] -> TMEM columns [pcol, pcol + 16); returns the fp32 row sum
-        auto cexp_store = [&](int lim, uint32_t pcol) -> float {
-          uint32_t w[16];
-          float sum;
-          if (lim >= 32) {
-            const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_ref, -m_ref);
-            uint64_t sum2 = pack2(0.f, 0.f);
+        auto max16m = [&](const uint32_t (&r)[16], int n, float m) -> float {   // the first n (< 16 possible) columns
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              float t0, t1;
-              unpack2(ffma2(pack2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), sc2, nm2), t0, t1);
-              float p0, p1;
-              if (POLY && (e & 3) == 3) {
-                ex2_poly2(t0, t1, p0, p1);
-              } else {
-                p0 = ex2_approx(t0);
-                p1 = ex2_approx(t1);
-              }
-              sum2 = fadd2(sum2, pack2(p0, p1));
-              w[e] = Op16<BF16>::pack(p0, p1);
-            }
-            float a0, a1;
-            unpack2(sum2, a0, a1);
-            sum = a0 + a1;
-          } else {
-            sum = 0.f;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const float s0 = 2 * e < lim ? __uint_as_float(r[2 * e]) : -INFINITY;
-              const float s1 = 2 * e + 1 < lim ? __uint_as_float(r[2 * e + 1]) : -INFINITY;
-              const float p0 = ex2_approx(fmaf(s0, sc, -m_ref));
-              const float p1 = ex2_approx(fmaf(s1, sc, -m_ref));
-              sum += p0 + p1;
-              w[e] = Op16<BF16>::pack(p0, p1);
-            }
-          }
-          tmem_st_32x16(pcol, w);
-          return sum;
+          for (int e = 0; e < 16; ++e)
+            if (e < n) m = fmaxf(m, __uint_as_float(r[e]));
+          return m;
         };
-        const uint32_t sa0 = s_addr + c0 * 32, sa1 = sa0 + 32, pa0 = p_addr + c0 * 16, pa1 = pa0 + 16;
+        // P chunk = exp2(S c - m_ref) of r[] -> TMEM columns [pcol, pcol + 8); adds to the packed fp32 row sum
+        auto exp16_store = [&](const uint32_t (&r)[16], uint32_t pcol, uint64_t& sum2) {
+          const uint64_t sc2 = pack2(sc, sc), nm2 = pack2(-m_ref, -m_ref);
+          uint32_t w[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float t0, t1;
+            unpack2(ffma2(pack2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), sc2, nm2), t0, t1);
+            float p0, p1;
+            if (POLY && (e & 3) == 3) {
+              ex2_poly2(t0, t1, p0, p1);
+            } else {
+              p0 = ex2_approx(t0);
+              p1 = ex2_approx(t1);
+            }
+            sum2 = fadd2(sum2, pack2(p0, p1));
+            w[e] = Op16<BF16>::pack(p0, p1);
+          }
+          tmem_st_32x8(pcol, w);
+        };
+        auto exp16m_store = [&](const uint32_t (&r)[16], int n, uint32_t pcol) -> float {   // columns >= n give P = 0
+          uint32_t w[8];
+          float sm = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float s0 = 2 * e < n ? __uint_as_float(r[2 * e]) : -INFINITY;
+            const float s1 = 2 * e + 1 < n ? __uint_as_float(r[2 * e + 1]) : -INFINITY;
+            const float p0 = ex2_approx(fmaf(s0, sc, -m_ref));
+            const float p1 = ex2_approx(fmaf(s1, sc, -m_ref));
+            sm += p0 + p1;
+            w[e] = Op16<BF16>::pack(p0, p1);
+          }
+          tmem_st_32x8(pcol, w);
+          return sm;
+        };
         if (j == 0) {
-          // first tile of the unit: the reference max = max over the whole first tile (both halves) and the leftover keys
+          // first tile of the unit: the reference max = max over the whole first tile (both halves).  (Taking it from the
+          // first 16 columns only and leaving the rest to the lazy rescale was measured 13 % SLOWER: the rescale path then
+          // runs in about every third unit.)
           float mx = -INFINITY;
-          if (lim0 > 0) {
-            tmem_ld_32x32(sa0, r);
-            tmem_ld_wait();
-            mx = cmax(lim0);
-          }
-          if (lim1 > 0) {
-            tmem_ld_32x32(sa1, r);
-            tmem_ld_wait();
-            mx = fmaxf(mx, cmax(lim1));
+          if (lim >= 64) {
+            tmem_ld_32x16(sa, ra);
+            tmem_ld_wait16(ra);
+            tmem_ld_32x16(sa + 16, rb);
+            mx = max16(ra, mx);
+            tmem_ld_wait16(rb);
+            tmem_ld_32x16(sa + 32, ra);
+            mx = max16(rb, mx);
+            tmem_ld_wait16(ra);
+            tmem_ld_32x16(sa + 48, rb);
+            mx = max16(ra, mx);
+            tmem_ld_wait16(rb);
+            mx = max16(rb, mx);
+          } else {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c)
+              if (16 * c < lim) {
+                tmem_ld_32x16(sa + 16 * c, ra);
+                tmem_ld_wait16(ra);
+                mx = max16m(ra, lim - 16 * c, mx);
+              }
           }
 #pragma unroll
           for (int e = 0; e < kExtraMax; ++e) mx = fmaxf(mx, s_x[e]);
           xput(2, mx);
-          pair_sync();
+          pair_sync();                           // (also: both halves have read s_x before either stores P)
           m_ref = fmaxf(mx, xget(2)) * sc;
+#pragma unroll
+          for (int e = 0; e < kExtraMax; ++e) {
+            if (e < n_extra) {
+              p_x[e] = ex2_approx(fmaf(s_x[e], sc, -m_ref));
+              if (half == 0) l += p_x[e];
+            }
+          }
         }
-        // ---- hot path: chunk 0: load -> max -> exp2 -> P store; chunk 1: load -> max; exchange of the tile max between
-        // the halves; S is released (Q K_{j+1}^T runs under the exponentials of chunk 1); chunk 1: exp2 -> P store
+        // ---- hot path: chunks 0-2: exp2 -> P store while the next chunk loads; chunk 3: max only; exchange of the tile
+        // max between the halves; S is released (Q K_{j+1}^T runs under the exponentials of chunk 3); chunk 3: exp2 -> P
         float mx_raw = -INFINITY, sum = 0.f;
+        uint64_t sum2 = pack2(0.f, 0.f);
         bool waited = false;
         auto wait_p_free = [&]() {
           if (!waited && g >= 1) {
@@ -658,21 +661,40 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
           waited = true;
         };
-        if (lim0 > 0) {
-          tmem_ld_32x32(sa0, r);
-          tmem_ld_wait();
-          mx_raw = cmax(lim0);
+        if (lim >= 64) {
+          tmem_ld_32x16(sa, ra);
+          tmem_ld_wait16(ra);
+          tmem_ld_32x16(sa + 16, rb);
+          mx_raw = max16(ra, mx_raw);
           wait_p_free();
-          alt_acquire();
-          sum = cexp_store(lim0, pa0);
+          exp16_store(ra, pa, sum2);
+          tmem_ld_wait16(rb);
+          tmem_ld_32x16(sa + 32, ra);
+          mx_raw = max16(rb, mx_raw);
+          exp16_store(rb, pa + 8, sum2);
+          tmem_ld_wait16(ra);
+          tmem_ld_32x16(sa + 48, rb);
+          mx_raw = max16(ra, mx_raw);
+          exp16_store(ra, pa + 16, sum2);
+          tmem_ld_wait16(rb);
+          mx_raw = max16(rb, mx_raw);
+        } else if (lim > 0) {                    // partial last tile of a ragged key count: chunk by chunk, masked
+          wait_p_free();
+#pragma unroll 1
+          for (int c = 0; c < 3; ++c)
+            if (16 * c < lim) {
+              tmem_ld_32x16(sa + 16 * c, ra);
+              tmem_ld_wait16(ra);
+              mx_raw = max16m(ra, lim - 16 * c, mx_raw);
+              sum += exp16m_store(ra, lim - 16 * c, pa + 8 * c);
+            }
+          if (lim > 48) {
+            tmem_ld_32x16(sa + 48, rb);
+            tmem_ld_wait16(rb);
+            mx_raw = max16m(rb, lim - 48, mx_raw);
+          }
         }
-        alt_release();                           // (every warp releases twice per tile, with or without valid keys)
         if (trace && g < 16) p.dbg[g * 12 + 3] = clock64();
-        if (lim1 > 0) {
-          tmem_ld_32x32(sa1, r);
-          tmem_ld_wait();
-          mx_raw = fmaxf(mx_raw, cmax(lim1));
-        }
         // lazy rescale: only when the tile's row max (over BOTH halves) exceeds the reference max by more than 2^8
         xput(g & 1, mx_raw);
         pair_sync();
@@ -681,40 +703,44 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (!__any_sync(0xffffffffu, need)) {    // both warps of the quadrant see the same rows, i.e. decide alike
           tc_fence_before();
           mbar_arrive(s_free);                   // this thread holds its last chunk in registers
-          if (lim1 > 0) {
-            wait_p_free();
-            alt_acquire();
-            sum += cexp_store(lim1, pa1);
-          }
-          alt_release();
+          if (lim >= 64) exp16_store(rb, pa + 24, sum2);
+          else if (lim > 48) sum += exp16m_store(rb, lim - 48, pa + 24);
         } else {
           wait_p_free();
-          alt_acquire();
           const float m_new = need ? mx_tile * sc : m_ref;
           const float f = ex2_approx(m_ref - m_new);   // 1 for rows that keep their reference
           m_ref = m_new;
           l *= f;
-          sum = 0.f;                             // P again with the new reference max: chunk 1 from registers ...
-          if (lim1 > 0) sum = cexp_store(lim1, pa1);
-          if (lim0 > 0) {                        // ... chunk 0 from S, which has not been released yet
-            tmem_ld_32x32(sa0, r);
-            tmem_ld_wait();
-            sum += cexp_store(lim0, pa0);
-          }
-          alt_release();
+#pragma unroll
+          for (int e = 0; e < kExtraMax; ++e) p_x[e] *= f;
+          sum = 0.f;                             // P again with the new reference max: chunk 3 from registers ...
+          sum2 = pack2(0.f, 0.f);
+          if (lim > 48) sum += exp16m_store(rb, lim - 48, pa + 24);
+#pragma unroll 1
+          for (int c = 0; c < 3; ++c)            // ... chunks 0-2 from S, which has not been released yet
+            if (16 * c < lim) {
+              tmem_ld_32x16(sa + 16 * c, ra);
+              tmem_ld_wait16(ra);
+              sum += exp16m_store(ra, lim - 16 * c, pa + 8 * c);
+            }
           tc_fence_before();
           mbar_arrive(s_free);
           if (j > 0) {                           // each half rescales its 32 columns of O
-            tmem_ld_32x32(o_addr + half * 32, r);
-            tmem_ld_wait();
-#pragma unroll
+#pragma unroll 1
             for (int hh = 0; hh < 2; ++hh) {
+              tmem_ld_32x16(o_addr + half * 32 + hh * 16, ra);
+              tmem_ld_wait16(ra);
               uint32_t w[16];
 #pragma unroll
-              for (int e = 0; e < 16; ++e) w[e] = __float_as_uint(__uint_as_float(r[hh * 16 + e]) * f);
+              for (int e = 0; e < 16; ++e) w[e] = __float_as_uint(__uint_as_float(ra[e]) * f);
               tmem_st_32x16(o_addr + half * 32 + hh * 16, w);
             }
           }
+        }
+        {
+          float a0, a1;
+          unpack2(sum2, a0, a1);
+          sum += a0 + a1;
         }
         if (trace && g < 16) p.dbg[g * 12 + 4] = clock64();
         l += sum;
@@ -726,32 +752,42 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       // ---- epilogue of the unit: (O + leftover keys) / l -> global; each half stores 32 of the 64 columns, in two
       // passes of 16 (the 80-register budget of a 384-thread CTA does not hold a 32-column row plus the extras)
-      if (alt && lane == 0 && n_tiles > 0) atomicSub(&alt_present[slot], 1);
       const int gt = g - 1;                      // trace row of the unit's last tile
       if (trace && gt >= 0 && gt < 16) p.dbg[gt * 12 + 5] = clock64();
-      if (n_tiles == 0) {
-        // no tensor-core tile at all (Nk <= kExtraMax): the reference max comes from the leftover keys alone
-        float mx = -INFINITY;
+      if (n_extra > 0) {
+        if (n_tiles == 0) {
+          // no tensor-core tile at all (Nk <= kExtraMax): the leftover keys are the whole softmax
+          float mx = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < kExtraMax; ++e) mx = fmaxf(mx, s_x[e]);
-        m_ref = mx * sc;
-      }
-      float p_x[kExtraMax];
+          for (int e = 0; e < kExtraMax; ++e) mx = fmaxf(mx, s_x[e]);
+          m_ref = mx * sc;
 #pragma unroll
-      for (int e = 0; e < kExtraMax; ++e) {
-        p_x[e] = e < n_extra ? ex2_approx(fmaf(s_x[e], sc, -m_ref)) : 0.f;   // fp32: no range issue whatever the score
-        if (half == 0) l += p_x[e];
+          for (int e = 0; e < kExtraMax; ++e) {
+            if (e < n_extra) {
+              p_x[e] = ex2_approx(fmaf(s_x[e], sc, -m_ref));
+              if (half == 0) l += p_x[e];
+            }
+          }
+        }
+        mbar_spin(&x_full[i & 1], (i >> 1) & 1);   // (landed long ago: makes the V_x rows visible to this thread)
       }
       xput(3, l);
       pair_sync();
       const float inv = 1.0f / (l + xget(3));
+      // (the staging tile is free once the previous unit's store has read it; this barrier sits in the shadow of the
+      // wait for the last P V below)
+      if (warp == 4 && lane == 0) tma_store_wait_read();
+      softmax_sync();
       if (n_tiles > 0) {
         mbar_spin(o_done, i & 1);
         tc_fence_after();
       }
       if (trace && gt >= 0 && gt < 16) p.dbg[gt * 12 + 6] = clock64();
-      const bool valid = (q0 + row) < p.row0;    // row0 = Nq, or the first row of the CUDA-core path
-      uint16_t* og = p.o + b * p.o_bs + static_cast<int64_t>(q0 + row) * p.ldo + static_cast<int64_t>(h) * kD + half * 32;
+      // The normalised tile goes to shared memory (rows of 128 B in the 128B-swizzle pattern of the tensor map) and
+      // leaves with ONE TMA store, asynchronously under the next unit: per-thread 16-byte stores to 3 KB-strided rows
+      // cost ~5000 cycles per unit in the load/store unit (32 lines per warp instruction).  The tensor map ends at row
+      // p.row0, so rows past Nq - or owned by the CUDA-core row path - are clipped by the TMA.
+      if (trace && gt >= 0 && gt < 16) p.dbg[gt * 12 + 9] = clock64();
       const uint8_t* xv = xk + kXBytes;
 #pragma unroll 1
       for (int sub = 0; sub < 2; ++sub) {
@@ -784,12 +820,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
           }
         }
-        if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(og + sub * 16);
 #pragma unroll
-          for (int e = 0; e < 2; ++e)
-            dst[e] = make_uint4(Op16<BF16>::pack(ov[8 * e] * inv, ov[8 * e + 1] * inv), Op16<BF16>::pack(ov[8 * e + 2] * inv, ov[8 * e + 3] * inv),
-                                Op16<BF16>::pack(ov[8 * e + 4] * inv, ov[8 * e + 5] * inv), Op16<BF16>::pack(ov[8 * e + 6] * inv, ov[8 * e + 7] * inv));
+        for (int e = 0; e < 2; ++e) {
+          const int chunk = half * 4 + sub * 2 + e;          // 16-byte chunk of the row's 128 bytes
+          *reinterpret_cast<uint4*>(sO + row * 128 + ((chunk ^ (row & 7)) << 4)) =
+              make_uint4(Op16<BF16>::pack(ov[8 * e] * inv, ov[8 * e + 1] * inv), Op16<BF16>::pack(ov[8 * e + 2] * inv, ov[8 * e + 3] * inv),
+                         Op16<BF16>::pack(ov[8 * e + 4] * inv, ov[8 * e + 5] * inv), Op16<BF16>::pack(ov[8 * e + 6] * inv, ov[8 * e + 7] * inv));
         }
       }
       if (n_tiles > 0) {
@@ -797,9 +833,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         mbar_arrive(o_free);                     // O has been read: the next unit's first P V may overwrite it
       }
       if (n_extra > 0) mbar_arrive(&x_empty[i & 1]);   // this thread is done with the unit's leftover-key rows
+      fence_proxy_async_smem();                        // the staged tile becomes visible to the TMA
+      softmax_sync();
+      if (warp == 4 && lane == 0) {
+        tma_store_4d(&tmO, sO, h * kD, 0, q0, b);
+        tma_store_commit();
+      }
       if (trace && gt >= 0 && gt < 16) p.dbg[gt * 12 + 10] = clock64();
     }
   }
+  if (warp == 4 && lane == 0) tma_store_wait_all();    // the last output tile has left shared memory and is written
   tc_fence_before();
   __syncthreads();
   if (p.dbg && threadIdx.x == 0) {
@@ -807,9 +850,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     p.dbg[192 + blockIdx.x * 4 + 3] = t;
   }
-  if (warp_g == 2) {
+  if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemColsAttn * SLOTS);
+    tmem_dealloc(tmem_base, kTmemColsAttn);
   }
 }
 
@@ -837,6 +880,7 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
   SATB_PROPAGATE(make_tmap_rows(&tq, q, q_cols, Nq, batch, ldq, q_bs, kQ));
   SATB_PROPAGATE(make_tmap_rows(&tk, k, k_cols, Nk, batch, ldk, k_bs, kK));
   SATB_PROPAGATE(make_tmap_rows(&tv, v, v_cols, Nk, batch, ldv, v_bs, kK));
+  CUtensorMap to;         // output tiles (TMA store), rows [0, row0): set below
   CUtensorMap tkx, tvx;   // the leftover keys (rows 128 n_tiles ...) as 16-row boxes
   SATB_PROPAGATE(make_tmap_rows(&tkx, k, k_cols, Nk, batch, ldk, k_bs, kXRows));
   SATB_PROPAGATE(make_tmap_rows(&tvx, v, v_cols, Nk, batch, ldv, v_bs, kXRows));
@@ -879,47 +923,39 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
   a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.q_bs = q_bs; a.k_bs = k_bs; a.v_bs = v_bs;
   a.scale_log2 = (1.0f / sqrtf(64.0f)) * 1.4426950408889634f;
   a.dbg = dbg;
+  SATB_REQUIRE(o_bs % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0, "attention output must be 16B aligned");
+  SATB_PROPAGATE(make_tmap_rows(&to, o, H * kD, a.row0 > 0 ? a.row0 : 1, batch, ldo, o_bs, kQ));
   const int row_tasks = batch * H * a.n_rows;
-  int grid = a.n_units > row_tasks ? a.n_units : row_tasks;   // pipelines with work
-  static int ctas_per_sm = -1, n_slots = -1, alternate = -1;
+  int grid = a.n_units > row_tasks ? a.n_units : row_tasks;
+  static int ctas_per_sm = -1;
   if (ctas_per_sm < 0) {
-    const char* e = getenv("SATB_ATTN_CTAS_PER_SM");   // 1: one pipeline per SM (A/B measurement of the SFU sharing)
+    const char* e = getenv("SATB_ATTN_CTAS_PER_SM");   // 1: one CTA per SM (A/B measurement of the SFU sharing)
     ctas_per_sm = (e && atoi(e) == 1) ? 1 : 2;
-    e = getenv("SATB_ATTN_SLOTS");                     // 1: two CTAs of one pipeline per SM; 2: one CTA of two pipelines
-    n_slots = e ? (atoi(e) == 1 ? 1 : 2) : kAttnSlotsDefault;
-    e = getenv("SATB_ATTN_ALT");                       // 0: the two pipelines of a CTA do not take turns on the SFU
-    alternate = e ? (atoi(e) != 0) : 1;
   }
-  a.alternate = alternate;
   const int slots = ctas_per_sm * device_sm_count();
   if (grid > slots) grid = slots;
   if (grid <= 0) return 0;
-  if (n_slots == 2) grid = (grid + 1) / 2;             // CTAs of two pipelines
+  a.step_bh = a.n_qt > 0 ? grid / a.n_qt : 0;
+  a.step_qt = a.n_qt > 0 ? grid % a.n_qt : 0;
   static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("SATB_ATTN_POLY");        // 0 / 1: A-B of the FMA-pipe exponentials
     poly = e ? (atoi(e) != 0) : kAttnPolyDefault;
   }
-  const int smem_bytes = attn_smem_bytes(n_slots);
   auto prepare = [&](auto kern) -> int {
-    SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     // two CTAs per SM need 2 x 98 KB: ask for the largest shared-memory carveout
     SATB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return 0;
   };
   auto go = [&](auto kern, PerDeviceOnce& once) -> int {
     if (once.first()) SATB_PROPAGATE(prepare(kern));
-    SATB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kAttnThreads * n_slots), smem_bytes, stream, tq, tk, tv, tkx, tvx, a));
+    SATB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kAttnThreads), kAttnSmem, stream, tq, tk, tv, tkx, tvx, to, a));
     return 0;
   };
-  static PerDeviceOnce o00, o01, o10, o11, t00, t01, t10, t11;
-  if (n_slots == 2) {
-    if (bf16) SATB_PROPAGATE(poly ? go(attn_tc_kernel<true, true, 2>, t11) : go(attn_tc_kernel<true, false, 2>, t10));
-    else SATB_PROPAGATE(poly ? go(attn_tc_kernel<false, true, 2>, t01) : go(attn_tc_kernel<false, false, 2>, t00));
-  } else {
-    if (bf16) SATB_PROPAGATE(poly ? go(attn_tc_kernel<true, true, 1>, o11) : go(attn_tc_kernel<true, false, 1>, o10));
-    else SATB_PROPAGATE(poly ? go(attn_tc_kernel<false, true, 1>, o01) : go(attn_tc_kernel<false, false, 1>, o00));
-  }
+  static PerDeviceOnce o00, o01, o10, o11;
+  if (bf16) SATB_PROPAGATE(poly ? go(attn_tc_kernel<true, true>, o11) : go(attn_tc_kernel<true, false>, o10));
+  else SATB_PROPAGATE(poly ? go(attn_tc_kernel<false, true>, o01) : go(attn_tc_kernel<false, false>, o00));
   count_launch();
   SATB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -928,7 +964,7 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
 // Debug: resident CTAs per SM the runtime reports for the attention kernel with `dyn_smem` bytes of dynamic shared
 // memory and the given carveout preference (percent, -1 = leave unchanged); tests / profiling only.
 int debug_attention_occupancy(int dyn_smem, int carveout_pct) {
-  auto kern = attn_tc_kernel<false, false, 1>;
+  auto kern = attn_tc_kernel<false, false>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem) != cudaSuccess) return -1;
   if (carveout_pct >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct);
   int nb = -1;

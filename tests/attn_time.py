@@ -9,6 +9,9 @@ sys.path.insert(0, os.path.join(ROOT, "friendly-stable-audio-tools_b200"))
 import torch
 from stable_audio_tools import _native as nat
 
+if os.environ.get("SATB_LIB"):          # A/B of kernel variants built side by side (tools only)
+    nat.LIB_PATH = os.path.abspath(os.environ["SATB_LIB"])
+
 B, H = int(os.environ.get("ATTN_B", "8")), 24
 tag = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("SATB_"))
 for N in [int(a) for a in sys.argv[1:]] or [1025]:

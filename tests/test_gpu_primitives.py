@@ -79,7 +79,10 @@ def test_tcgen05_linear_vs_torch(M, N, K, bf16):
                                            (1, 3, 3, 65, 191), (1, 24, 24, 300, 300),
                                            # 2 ragged query rows (CUDA-core row path) x 1 leftover key; only row-path rows;
                                            # no tensor-core key tile at all (2 keys); many units per CTA
-                                           (1, 2, 2, 130, 257), (1, 2, 1, 2, 130), (2, 4, 2, 128, 2), (3, 24, 24, 1024, 384)])
+                                           (1, 2, 2, 130, 257), (1, 2, 1, 2, 130), (2, 4, 2, 128, 2), (3, 24, 24, 1024, 384),
+                                           # small batch at the SA-Open length: the 1025th query row rides as a partial
+                                           # tile (no row path), one leftover key, several units per CTA back to back
+                                           (2, 24, 24, 1025, 1025)])
 def test_attention_vs_oracle(B, H, Hkv, Nq, Nk):
     """softmax(q k^T / 8) v vs the oracle's einsum path (models/transformer.py:510-536), fp16 operands."""
     from oracle.dit_oracle import attention_core
@@ -98,12 +101,15 @@ def test_attention_vs_oracle(B, H, Hkv, Nq, Nk):
     assert rel_l2(o.float().cpu(), ref) < 2e-3
 
 
-def test_attention_lazy_rescale_path_monotone_scores():
+@pytest.mark.parametrize("Nk", [700, 641])
+def test_attention_lazy_rescale_path_monotone_scores(Nk):
     """Scores that keep growing along the key axis force the reference max to move in (almost)
-    every 64-key tile: exercises the O rescale + P recomputation path of the tcgen05 kernel."""
+    every 64-key tile: exercises the O rescale + P recomputation path of the tcgen05 kernel.  Nk = 641 = 5 x 128 + 1:
+    the leftover key (scores by a 16-column MMA, exponential kept in registers) is the row maximum of head 0 and is
+    carried through every rescale of head 1."""
     from oracle.dit_oracle import attention_core
     nat = _native()
-    B, H, Nq, Nk = 1, 2, 200, 700
+    B, H, Nq = 1, 2, 200
     torch.manual_seed(0)
     q = torch.zeros(B, Nq, H * 64)
     k = torch.zeros(B, Nk, H * 64)
