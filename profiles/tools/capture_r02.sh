@@ -10,7 +10,7 @@ timeout 600 ncu --metrics $M --clock-control none --kernel-name-base demangled -
     --log-file gpurun_out/r02_launches_step.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph \
     > gpurun_out/r02_launches_step.out 2>&1
 # 2. --set full of the dominant kernels at the bench shapes (depth-2 model, same 8 x 1025 rows)
-for spec in "attn:regex:attn_tc_kernel:3" "ffin:regex:EpiSwiglu:2" "qkv:regex:EpiQkvRope:2" "ln:regex:layernorm_kernel:4"; do
+for spec in "attn:regex:attn_tc_kernel:4" "ffin:regex:EpiSwiglu:2" "qkv:regex:EpiQkvRope:2" "ln:regex:layernorm_kernel:4"; do
   name=${spec%%:*}; rest=${spec#*:}; kern=${rest%:*}; skip=${rest##*:}
   timeout 400 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k $kern -s $skip -c 1 \
       -f -o gpurun_out/r02_$name python tests/prof_step.py dit > gpurun_out/r02_$name.log 2>&1
