@@ -1097,8 +1097,97 @@ struct EpiConv {
     *idx = (static_cast<size_t>(c.batch) * p.L_out + (ok ? lo : 0)) * p.cout + sg.co;
     return ok;
   }
+  // ---- fast path.  The general code below costs ~120 instructions per 4-element segment, of which ~55 % are index
+  // arithmetic, bounds tests and branches on the (launch-uniform) Params flags (ncu source page of the stride-2
+  // transposed convolution, profiles/r02_ncu_convT_s2.txt: 30 instructions per element; the 128-channel layers are
+  // bound by exactly this epilogue).  For a chunk whose 32 rows all exist - every chunk but the ragged ends of an item -
+  // the 8 segments of a lane are idx0 + i * stride, so one index, one bounds test and one branch per chunk do;
+  // the flags become template parameters.  Conditions: 16-bit raw streams (or none), a 16-bit output, no lo copy.
+  struct Plan {
+    size_t idx0;      // element index of segment 0
+    int stride;       // elements between consecutive segments (4 rows)
+    bool fast;        // warp-uniform
+    int co;
+  };
+  __device__ static __forceinline__ Plan plan_of(const Params& p, const EpiCtx& c) {
+    const Seg sg = seg_of(p, c);
+    const int l_first = c.l0 + (c.lane >> 3), l_last = l_first + 28;
+    const int lo_first = l_first * p.up + sg.phase - p.pad, lo_last = l_last * p.up + sg.phase - p.pad;
+    const bool ok = l_last < c.L && lo_first >= 0 && lo_last < p.L_out;
+    // the three flag combinations the 16-bit decoder / encoder runs: Snake-activated 16-bit output, with (skip + raw out),
+    // (raw out) or neither
+    const bool flags = p.s16_out != nullptr && p.sn_a != nullptr && p.s16_lo_out == nullptr &&
+                       (p.raw16 != 0 || (p.resid == nullptr && p.raw_out == nullptr)) && (p.resid == nullptr || p.raw_out != nullptr);
+    Plan pl;
+    pl.fast = flags && __all_sync(0xffffffffu, ok);
+    pl.idx0 = (static_cast<size_t>(c.batch) * p.L_out + (ok ? lo_first : 0)) * p.cout + sg.co;
+    pl.stride = 4 * p.up * p.cout;
+    pl.co = sg.co;
+    return pl;
+  }
+  template <bool RESID, bool RAWOUT, bool SNAKE>
+  __device__ static __forceinline__ void finish_fast(const Params& p, const EpiCtx& c, const Plan& pl, const uint32_t (&r)[32],
+                                                     const float4 (&rs)[8]) {
+    const uint32_t st = smem_u32(c.stage);
+    const int g = c.lane & 7, r0 = c.lane >> 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sts128(st + (c.lane * 36 + 4 * j) * 4, r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    __syncwarp();
+    ulonglong2 b2 = make_ulonglong2(0ull, 0ull), a2 = b2, ib2 = b2;   // (x,y) and (z,w) pairs; 0 bits = 0.f
+    if (p.bias) b2 = __ldg(reinterpret_cast<const ulonglong2*>(p.bias + pl.co));
+    if (SNAKE) {
+      a2 = __ldg(reinterpret_cast<const ulonglong2*>(p.sn_a + pl.co));
+      ib2 = __ldg(reinterpret_cast<const ulonglong2*>(p.sn_ib + pl.co));
+    }
+    uint16_t* raw_o = static_cast<uint16_t*>(p.raw_out) + pl.idx0;
+    uint16_t* s_o = static_cast<uint16_t*>(p.s16_out) + pl.idx0;
+    uint32_t ld_addr = st + (r0 * 36 + 4 * g) * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const ulonglong2 acc = lds128_b64x2(ld_addr);   // (reading all eight segments back first was not faster)
+      ld_addr += 4 * 36 * 4;
+      uint64_t v01 = f2_add(acc.x, b2.x), v23 = f2_add(acc.y, b2.y);
+      if (RESID) {
+        const float2 lo = Op16<BF16>::unpack(__float_as_uint(rs[i].x)), hi = Op16<BF16>::unpack(__float_as_uint(rs[i].y));
+        v01 = f2_add(v01, f2_pack(lo.x, lo.y));
+        v23 = f2_add(v23, f2_pack(hi.x, hi.y));
+      }
+      if (RAWOUT) {
+        float y0, y1, y2, y3;
+        f2_unpack(v01, y0, y1);
+        f2_unpack(v23, y2, y3);
+        *reinterpret_cast<uint2*>(raw_o) = make_uint2(Op16<BF16>::pack(y0, y1), Op16<BF16>::pack(y2, y3));
+        raw_o += pl.stride;
+      }
+      if (SNAKE) {
+        v01 = snake_fast2(v01, a2.x, ib2.x);
+        v23 = snake_fast2(v23, a2.y, ib2.y);
+      }
+      float x0, x1, x2, x3;
+      f2_unpack(v01, x0, x1);
+      f2_unpack(v23, x2, x3);
+      *reinterpret_cast<uint2*>(s_o) = make_uint2(Op16<BF16>::pack(x0, x1), Op16<BF16>::pack(x2, x3));
+      s_o += pl.stride;
+    }
+    __syncwarp();
+  }
   // Issue the residual (skip) loads of a chunk; they can be left in flight across other work.
   __device__ static __forceinline__ void prefetch(const Params& p, const EpiCtx& c, float4 (&rs)[8]) {
+    {
+      const Plan pl = plan_of(p, c);
+      if (pl.fast) {
+        if (p.resid) {
+          const uint16_t* rp = static_cast<const uint16_t*>(p.resid) + pl.idx0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint2 u = *reinterpret_cast<const uint2*>(rp);     // the loaded BITS (converted in finish())
+            rp += pl.stride;
+            rs[i] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), 0.f, 0.f);
+          }
+        }
+        return;
+      }
+    }
     const Seg sg = seg_of(p, c);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -1119,6 +1208,15 @@ struct EpiConv {
   }
   __device__ static __forceinline__ void finish(const Params& p, const EpiCtx& c, const uint32_t (&r)[32],
                                                 const float4 (&rs)[8]) {
+    {
+      const Plan pl = plan_of(p, c);
+      if (pl.fast) {
+        if (p.resid) finish_fast<true, true, true>(p, c, pl, r, rs);
+        else if (p.raw_out) finish_fast<false, true, true>(p, c, pl, r, rs);
+        else finish_fast<false, false, true>(p, c, pl, r, rs);
+        return;
+      }
+    }
     float* st = c.stage;
     const int g = c.lane & 7, r0 = c.lane >> 3;
     {

@@ -7,6 +7,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "friendly-stable-audio-tools_b200"))
 import torch
+from stable_audio_tools import _native as nat
+if os.environ.get("SATB_LIB"):          # A/B of kernel variants built side by side (tools only)
+    nat.LIB_PATH = os.path.abspath(os.environ["SATB_LIB"])
 from oracle import oobleck_oracle as oo
 from stable_audio_tools.models.autoencoders import OobleckDecoder
 
