@@ -1114,10 +1114,11 @@ struct EpiConv {
     const int l_first = c.l0 + (c.lane >> 3), l_last = l_first + 28;
     const int lo_first = l_first * p.up + sg.phase - p.pad, lo_last = l_last * p.up + sg.phase - p.pad;
     const bool ok = l_last < c.L && lo_first >= 0 && lo_last < p.L_out;
-    // the three flag combinations the 16-bit decoder / encoder runs: Snake-activated 16-bit output, with (skip + raw out),
-    // (raw out) or neither
+    // the flag combinations the 16-bit decoder / encoder runs: Snake-activated 16-bit output, with or without the skip
+    // input and the raw output.  (Moving the general path out of line instead - __noinline__ - made the decode 40-90 %
+    // SLOWER: the call sites force the chunk registers through local memory.)
     const bool flags = p.s16_out != nullptr && p.sn_a != nullptr && p.s16_lo_out == nullptr &&
-                       (p.raw16 != 0 || (p.resid == nullptr && p.raw_out == nullptr)) && (p.resid == nullptr || p.raw_out != nullptr);
+                       (p.raw16 != 0 || (p.resid == nullptr && p.raw_out == nullptr));
     Plan pl;
     pl.fast = flags && __all_sync(0xffffffffu, ok);
     pl.idx0 = (static_cast<size_t>(c.batch) * p.L_out + (ok ? lo_first : 0)) * p.cout + sg.co;
@@ -1211,9 +1212,13 @@ struct EpiConv {
     {
       const Plan pl = plan_of(p, c);
       if (pl.fast) {
-        if (p.resid) finish_fast<true, true, true>(p, c, pl, r, rs);
-        else if (p.raw_out) finish_fast<false, true, true>(p, c, pl, r, rs);
-        else finish_fast<false, false, true>(p, c, pl, r, rs);
+        if (p.resid) {
+          if (p.raw_out) finish_fast<true, true, true>(p, c, pl, r, rs);
+          else finish_fast<true, false, true>(p, c, pl, r, rs);    // last unit of a block: nobody reads its raw output
+        } else {
+          if (p.raw_out) finish_fast<false, true, true>(p, c, pl, r, rs);
+          else finish_fast<false, false, true>(p, c, pl, r, rs);
+        }
         return;
       }
     }
