@@ -363,13 +363,18 @@ int run_conv_gemm(SatbOobleck* h, const ConvW& cw, const void* in16, int B, int 
   }
   auto get_b = [&](int box, const CUtensorMap** out) -> int { return get_tmap_b(h, cw, b_rows, box, out); };
   const CUtensorMap* tb;
-  if (s.N >= 256 && s.L >= 512 && gemm_use_2cta()) {
+  // CTA pairs pay off where the mainloop is long (k7 / strided convolutions: >= 3 taps).  The 1x1 convolutions and
+  // the transposed convolutions (2 taps) are epilogue-bound, and there the per-tile hand-offs between the two CTAs
+  // cost more than the halved B traffic saves: single CTAs measured 495 vs 578 us (stride 2, 128 channels), 159 vs
+  // 185 us (stride 4, 512 -> 256), 33 vs 40 and 88 vs 107 us (1x1 + skip at 1024 / 512 channels).
+  const bool pair = gemm_use_2cta() && s.L >= 512 && s.n_taps >= 3;
+  if (s.N >= 256 && pair) {
     SATB_PROPAGATE(get_b(128, &tb));   // CTA pair: each CTA loads half of the 256-wide B tile
     return launch_gemm_2cta<Epi, 256, BF16>(ta, *tb, s, ep, st, ta2);
   } else if (s.N >= 256) {
     SATB_PROPAGATE(get_b(256, &tb));
     return launch_gemm<Epi, 256, BF16>(ta, *tb, s, ep, st, ta2);
-  } else if (s.N == 128 && s.L >= 512 && gemm_use_2cta()) {
+  } else if (s.N == 128 && pair) {
     SATB_PROPAGATE(get_b(64, &tb));    // CTA pair on 256 x 128 tiles: halves the B traffic of the 128-channel layers
     return launch_gemm_2cta<Epi, 128, BF16>(ta, *tb, s, ep, st, ta2);
   } else if (s.N > 64) {
