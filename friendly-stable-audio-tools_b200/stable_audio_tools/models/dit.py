@@ -47,6 +47,8 @@ class DiffusionTransformer(nn.Module):
             raise NotImplementedError("only transformer_type='continuous_transformer' is on the native hot path "
                                       "(the reference's x-transformers branch needs an un-vendored dependency)")
         if prepend_cond_dim > 0 and global_cond_type != "prepend":
+            # (the reference itself mis-handles this pair: prepend_length is only set in "prepend" mode, dit.py:185-197,
+            # so its output keeps the prepended positions - L + n_prepend columns, a shape no sampler can consume)
             raise NotImplementedError("prepend_cond with global_cond_type='adaLN' is not on the native hot path")
         if patch_size < 1:
             raise ValueError("patch_size must be >= 1")
