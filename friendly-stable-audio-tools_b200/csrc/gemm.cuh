@@ -1052,26 +1052,36 @@ __device__ __forceinline__ uint64_t snake_fast2(uint64_t v, uint64_t a, uint64_t
 //   s16_out[pos, co] = 16-bit( snake_next(y) )       the NEXT layer's activation, fused here
 // Transposed convolutions (:102-105) run as a 2-tap GEMM over N = up*cout columns
 // (column = phase*cout + co): output position = l*up + phase - pad.
-template <bool BF16>
+struct EpiConvParams {
+  const float* bias;    // [cout] or null
+  const void* resid;    // raw skip stream [B*L_out, cout] (fp32, or 16-bit when raw16) or null
+  void* raw_out;        // raw stream out, same type, or null
+  void* s16_out;        // 16-bit [B*L_out, cout] or null
+  const float* sn_a;    // [cout] e^alpha of the consumer's Snake, or null (plain cast)
+  const float* sn_ib;   // [cout] 1/(e^beta + 1e-9)
+  int cout;
+  int L_out;            // output positions per batch item
+  int up;               // transposed-conv stride (1 = ordinary conv)
+  int pad;              // transposed-conv padding
+  void* s16_lo_out;     // split-operand mode: 16-bit(y' - 16-bit(y')) next to s16_out (y' = the Snake-activated value), or null
+  int raw16;            // 1: the raw (un-activated) stream is stored in the 16-bit operand type instead of fp32:
+                        // 8 instead of 12 bytes per element and channel through a fused ResidualUnit (the sums
+                        // are still formed in fp32; only the value carried to the next unit's skip is rounded)
+};
+// MASKED = true: the kernel carries ONLY the lean path (one index per chunk, per-segment validity as a bit mask, Snake and
+// 16-bit raw streams unconditional) - for launches whose Params satisfy fast_flags(); the host picks the instantiation
+// (oobleck.cu run_conv_gemm).  Compiled next to the general path in one kernel the lean path pays ~200 bytes of spills
+// in the persistent GEMM kernels (long-scoreboard stalls on the reloads, profiles/r02_ncu_convT_s2.txt).
+template <bool BF16, bool MASKED = false>
 struct EpiConv {
   static constexpr int kCols = 32;
   static constexpr int kStageBytes = 32 * 36 * 4;   // per-warp [32 rows][32 + 4 pad] fp32 transpose tile
-  struct Params {
-    const float* bias;    // [cout] or null
-    const void* resid;    // raw skip stream [B*L_out, cout] (fp32, or 16-bit when raw16) or null
-    void* raw_out;        // raw stream out, same type, or null
-    void* s16_out;        // 16-bit [B*L_out, cout] or null
-    const float* sn_a;    // [cout] e^alpha of the consumer's Snake, or null (plain cast)
-    const float* sn_ib;   // [cout] 1/(e^beta + 1e-9)
-    int cout;
-    int L_out;            // output positions per batch item
-    int up;               // transposed-conv stride (1 = ordinary conv)
-    int pad;              // transposed-conv padding
-    void* s16_lo_out;     // split-operand mode: 16-bit(y' - 16-bit(y')) next to s16_out (y' = the Snake-activated value), or null
-    int raw16;            // 1: the raw (un-activated) stream is stored in the 16-bit operand type instead of fp32:
-                          // 8 instead of 12 bytes per element and channel through a fused ResidualUnit (the sums
-                          // are still formed in fp32; only the value carried to the next unit's skip is rounded)
-  };
+  typedef EpiConvParams Params;
+  // Snake-activated 16-bit output, raw streams (if any) in the 16-bit type, no lo copy: what the default fp16 decode runs
+  __host__ __device__ static bool fast_flags(const Params& p) {
+    return p.s16_out != nullptr && p.sn_a != nullptr && p.s16_lo_out == nullptr &&
+           (p.raw16 != 0 || (p.resid == nullptr && p.raw_out == nullptr));
+  }
   // Warp-cooperative: the accumulator chunk (thread = row, 32 columns) is transposed through the
   // per-warp smem tile so that every global access is coalesced (8 lanes x 16 B = one 128 B row
   // segment, 4 rows per instruction) and each lane needs the per-channel parameters of only 4 channels.
@@ -1114,11 +1124,9 @@ struct EpiConv {
     const int l_first = c.l0 + (c.lane >> 3), l_last = l_first + 28;
     const int lo_first = l_first * p.up + sg.phase - p.pad, lo_last = l_last * p.up + sg.phase - p.pad;
     const bool ok = l_last < c.L && lo_first >= 0 && lo_last < p.L_out;
-    // the flag combinations the 16-bit decoder / encoder runs: Snake-activated 16-bit output, with or without the skip
-    // input and the raw output.  (Moving the general path out of line instead - __noinline__ - made the decode 40-90 %
-    // SLOWER: the call sites force the chunk registers through local memory.)
-    const bool flags = p.s16_out != nullptr && p.sn_a != nullptr && p.s16_lo_out == nullptr &&
-                       (p.raw16 != 0 || (p.resid == nullptr && p.raw_out == nullptr));
+    // (Moving the general path out of line instead - __noinline__ - made the decode 40-90 % SLOWER: the call sites
+    // force the chunk registers through local memory.)
+    const bool flags = fast_flags(p);
     Plan pl;
     pl.fast = flags && __all_sync(0xffffffffu, ok);
     pl.idx0 = (static_cast<size_t>(c.batch) * p.L_out + (ok ? lo_first : 0)) * p.cout + sg.co;
@@ -1172,8 +1180,102 @@ struct EpiConv {
     }
     __syncwarp();
   }
+  // ---- MASKED kernels: the same arithmetic for every chunk, ragged ones included (bit i of the mask = segment i exists)
+  struct MPlan {
+    long long idx0;   // element index of segment 0 (may point before the buffer when that segment does not exist)
+    int stride;
+    uint32_t mask;
+    int co;
+  };
+  __device__ static __forceinline__ MPlan mplan_of(const Params& p, const EpiCtx& c) {
+    const Seg sg = seg_of(p, c);
+    const int l0 = c.l0 + (c.lane >> 3);
+    const int lo0 = l0 * p.up + sg.phase - p.pad;
+    MPlan pl;
+    pl.mask = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int l = l0 + 4 * i, lo = lo0 + 4 * i * p.up;
+      if (l < c.L && lo >= 0 && lo < p.L_out) pl.mask |= 1u << i;
+    }
+    pl.idx0 = (static_cast<long long>(c.batch) * p.L_out + lo0) * p.cout + sg.co;
+    pl.stride = 4 * p.up * p.cout;
+    pl.co = sg.co;
+    return pl;
+  }
+  __device__ static __forceinline__ void prefetch_masked(const Params& p, const EpiCtx& c, float4 (&rs)[8]) {
+    if (p.resid) {
+      const MPlan pl = mplan_of(p, c);
+      const uint16_t* rp = static_cast<const uint16_t*>(p.resid) + pl.idx0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint2 u = make_uint2(0u, 0u);
+        if ((pl.mask >> i) & 1u) u = *reinterpret_cast<const uint2*>(rp);     // the loaded BITS (converted in finish)
+        rp += pl.stride;
+        rs[i] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), 0.f, 0.f);
+      }
+    }
+  }
+  template <bool RESID, bool RAWOUT>
+  __device__ static __forceinline__ void finish_masked_t(const Params& p, const EpiCtx& c, const uint32_t (&r)[32],
+                                                         const float4 (&rs)[8]) {
+    const MPlan pl = mplan_of(p, c);
+    const uint32_t st = smem_u32(c.stage);
+    const int g = c.lane & 7, r0 = c.lane >> 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sts128(st + (c.lane * 36 + 4 * j) * 4, r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    __syncwarp();
+    ulonglong2 b2 = make_ulonglong2(0ull, 0ull);
+    if (p.bias) b2 = __ldg(reinterpret_cast<const ulonglong2*>(p.bias + pl.co));
+    const ulonglong2 a2 = __ldg(reinterpret_cast<const ulonglong2*>(p.sn_a + pl.co));
+    const ulonglong2 ib2 = __ldg(reinterpret_cast<const ulonglong2*>(p.sn_ib + pl.co));
+    uint16_t* raw_o = static_cast<uint16_t*>(p.raw_out) + pl.idx0;
+    uint16_t* s_o = static_cast<uint16_t*>(p.s16_out) + pl.idx0;
+    uint32_t ld_addr = st + (r0 * 36 + 4 * g) * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const ulonglong2 acc = lds128_b64x2(ld_addr);
+      ld_addr += 4 * 36 * 4;
+      const bool ok = (pl.mask >> i) & 1u;
+      uint64_t v01 = f2_add(acc.x, b2.x), v23 = f2_add(acc.y, b2.y);
+      if (RESID) {
+        const float2 lo = Op16<BF16>::unpack(__float_as_uint(rs[i].x)), hi = Op16<BF16>::unpack(__float_as_uint(rs[i].y));
+        v01 = f2_add(v01, f2_pack(lo.x, lo.y));
+        v23 = f2_add(v23, f2_pack(hi.x, hi.y));
+      }
+      if (RAWOUT) {
+        float y0, y1, y2, y3;
+        f2_unpack(v01, y0, y1);
+        f2_unpack(v23, y2, y3);
+        if (ok) *reinterpret_cast<uint2*>(raw_o) = make_uint2(Op16<BF16>::pack(y0, y1), Op16<BF16>::pack(y2, y3));
+        raw_o += pl.stride;
+      }
+      v01 = snake_fast2(v01, a2.x, ib2.x);
+      v23 = snake_fast2(v23, a2.y, ib2.y);
+      float x0, x1, x2, x3;
+      f2_unpack(v01, x0, x1);
+      f2_unpack(v23, x2, x3);
+      if (ok) *reinterpret_cast<uint2*>(s_o) = make_uint2(Op16<BF16>::pack(x0, x1), Op16<BF16>::pack(x2, x3));
+      s_o += pl.stride;
+    }
+    __syncwarp();
+  }
+  __device__ static __forceinline__ void finish_masked(const Params& p, const EpiCtx& c, const uint32_t (&r)[32],
+                                                       const float4 (&rs)[8]) {
+    if (p.resid) {
+      if (p.raw_out) finish_masked_t<true, true>(p, c, r, rs);
+      else finish_masked_t<true, false>(p, c, r, rs);
+    } else {
+      if (p.raw_out) finish_masked_t<false, true>(p, c, r, rs);
+      else finish_masked_t<false, false>(p, c, r, rs);
+    }
+  }
   // Issue the residual (skip) loads of a chunk; they can be left in flight across other work.
   __device__ static __forceinline__ void prefetch(const Params& p, const EpiCtx& c, float4 (&rs)[8]) {
+    if constexpr (MASKED) {
+      prefetch_masked(p, c, rs);
+      return;
+    }
     {
       const Plan pl = plan_of(p, c);
       if (pl.fast) {
@@ -1209,6 +1311,10 @@ struct EpiConv {
   }
   __device__ static __forceinline__ void finish(const Params& p, const EpiCtx& c, const uint32_t (&r)[32],
                                                 const float4 (&rs)[8]) {
+    if constexpr (MASKED) {
+      finish_masked(p, c, r, rs);
+      return;
+    }
     {
       const Plan pl = plan_of(p, c);
       if (pl.fast) {

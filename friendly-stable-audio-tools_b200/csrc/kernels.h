@@ -13,6 +13,7 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* o, in
 int debug_attention_occupancy(int dyn_smem, int carveout_pct);
 // debugging switches (environment variables; the defaults are the production path)
 bool conv_halo_enabled();     // SATB_CONV_HALO=off: generic 7-tap loads for the final conv (A/B debugging)
+bool conv_epi_masked();        // SATB_CONV_EPI=general keeps the combined-epilogue GEMM kernels for the 16-bit convolutions (A/B debugging)
 bool resunit_use_fused();      // SATB_RESUNIT=unfused runs the 128-channel ResidualUnits as two GEMM launches (A/B debugging)
 bool gemm_use_2cta();          // SATB_GEMM=1cta disables the CTA-pair GEMM (A/B debugging)
 bool ln_fold_enabled();        // SATB_LN=fold: LayerNorm folded into the GEMM epilogues (A/B; measured slower, off by default)

@@ -333,6 +333,11 @@ int get_tmap_b(SatbOobleck* h, const ConvW& cw, int b_rows, int box, const CUten
 template <class Epi, bool BF16>
 int run_conv_gemm(SatbOobleck* h, const ConvW& cw, const void* in16, int B, int L_in, int kind, int dil, int factor,
                   const typename Epi::Params& ep, cudaStream_t st) {
+  // the default 16-bit decode / encode runs the lean-epilogue instantiation of the GEMM kernels (EpiConv<.., MASKED>)
+  if constexpr (std::is_same<Epi, EpiConv<BF16, false>>::value) {
+    if (Epi::fast_flags(ep) && conv_epi_masked())
+      return run_conv_gemm<EpiConv<BF16, true>, BF16>(h, cw, in16, B, L_in, kind, dil, factor, ep, st);
+  }
   GemmShape s;
   s.batches = B;
   s.b_static = 1;   // folded weight-norm weights, written at finalize time

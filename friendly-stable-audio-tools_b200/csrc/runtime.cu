@@ -56,6 +56,15 @@ bool conv_halo_enabled() {
   return v == 1;
 }
 
+bool conv_epi_masked() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SATB_CONV_EPI");    // "general": the combined fast + general epilogue kernels (A/B debugging)
+    v = (e && std::string(e) == "general") ? 0 : 1;
+  }
+  return v == 1;
+}
+
 bool resunit_use_fused() {
   static int v = -1;
   if (v < 0) {
